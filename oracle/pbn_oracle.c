@@ -1,0 +1,459 @@
+/*
+ * pbn_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, byte-per-node CPU restatement of the reference's hot path
+ * (jakub-zarzycki2022/gym-PBN-stac, pure Python).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load it; the product
+ * (gym-pbn-stac_b200/) never does and fails loudly without its CUDA library.
+ *
+ * Parity pinning: the reference's own tests hold no golden vectors for this path
+ * (SURVEY.md §8c), so the oracle is pinned against outputs of the reference itself,
+ * recorded in this container by oracle/make_golden.py under replayed draws and committed
+ * under tests/golden/ (tests/test_oracle_golden.py).
+ *
+ * Two draw sources:
+ *   REPLAY — consumes recorded CPython `random` / numpy.random draws in the reference's exact
+ *            order and compares in float64 exactly as the reference does;
+ *   PHILOX — Philox4x32-10 keyed by (seed; epoch, global env id), integer 31-bit thresholds.
+ *            Same structure, integer arithmetic; this is the stream the CUDA kernels use, so
+ *            GPU-vs-oracle comparisons in this mode are bit-exact at any size.
+ *
+ * Each function cites the reference file:line it follows.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_TT 0   /* truth-table PBN / PBCN  (gym_PBN/envs/common) */
+#define ORC_PRED 1 /* Bittner predictor graph (gym_PBN/envs/bittner/base.py) */
+
+typedef struct {
+    int32_t kind, n, first; /* first updatable node: 1 for PBN.step (common/pbn.py:90), 0 for Graph.step (base.py:308) */
+    /* ORC_TT: node i reads inputs tt_in[tt_in_off[i] .. tt_in_off[i+1]) (ascending node index, first = MSB,
+       common/node.py:31-32) and P(next=1) = tt_prob[tt_tab_off[i] + idx] */
+    const int32_t *tt_in_off, *tt_in, *tt_tab_off;
+    const double *tt_prob;
+    /* ORC_PRED: node i owns predictors pr_off[i] .. pr_off[i+1); predictor q reads nodes pr_in[4q..4q+3]
+       (3 inputs then the node itself, base.py:100-104), LUT bit (x0<<3|x1<<2|x2<<1|x3) = [X.A >= 0] (base.py:110-118),
+       pr_cum[q] = cumulative COD (base.py:30-45), pr_codsum[i] = CODsum */
+    const int32_t *pr_off, *pr_in;
+    const uint16_t *pr_lut;
+    const double *pr_cum, *pr_codsum;
+    /* PHILOX mode: 31-bit thresholds filled by orc_fill_thresholds (caller-allocated, same shapes as tt_prob / pr_cum) */
+    uint32_t *tt_thr, *pr_thr;
+} OrcNet;
+
+#define ORC_PHILOX 0
+#define ORC_REPLAY 1
+
+typedef struct {
+    int32_t mode;
+    uint32_t epoch;
+    uint64_t seed;
+    const int32_t *ints; /* replay: row e = ints + e*int_stride */
+    const double *dbls;
+    int64_t int_stride, dbl_stride;
+    int64_t *used; /* optional out [B][2]: ints/doubles (replay) or u32 draws/0 (philox) consumed */
+} OrcDraws;
+
+/* env kinds — one per reference env class on the hot path */
+#define ORC_ENV_PBN 0      /* PBNEnv              pbn_env.py:125-188 */
+#define ORC_ENV_PBCN 1     /* PBCNEnv             pbcn_env.py:52-80 */
+#define ORC_ENV_TARGET 2   /* PBNTargetEnv        pbn_target.py:241-326 */
+#define ORC_ENV_MULTI 3    /* PBNTargetMultiEnv   pbn_target_multi.py:119-225 */
+#define ORC_ENV_PBN_SD 4   /* PBNSampledDataEnv   sampled_data.py:52-88 */
+#define ORC_ENV_PBCN_SD 5  /* PBCNSampledDataEnv  sampled_data.py:139-189 */
+
+typedef struct {
+    int32_t kind, horizon, max_inner;
+    int32_t force;        /* PBNTargetEnv.step(force=True): exactly one update, pbn_target.py:270 */
+    int32_t dedup;        /* multi: tensor actions are unique()'d, lists are not, pbn_target_multi.py:120-121 */
+    int32_t control_write;/* PBCN: 0 = reference (apply_control has no effect on dynamics, Q4); 1 = write control into state[0:M] */
+    int32_t n_control;
+    int32_t successful_reward, wrong_attractor_cost; /* PBCNEnv._get_reward, pbcn_env.py:52-65 */
+    /* cubes: attractor a owns cubes att_off[a] .. att_off[a+1); cube c = cube[c*n .. ), values 0/1/2('*') */
+    int32_t n_att;
+    const int32_t *att_off;
+    const int8_t *cube;
+    /* PBN/PBCN target set = full states, tgt_off = first cube of the target list, n_tgt entries (pbn_env.py:55-59) */
+    int32_t tgt_first, n_tgt;
+} OrcEnv;
+
+/* ------------------------------------------------------------------------------------ Philox4x32-10 */
+static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+    for (int r = 0; r < 10; r++) {
+        philox_round(c, k);
+        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+    }
+    memcpy(out, c, sizeof c);
+}
+
+typedef struct {
+    int mode;
+    uint32_t key[2], ctr[4], buf[4];
+    int have;
+    const int32_t *ip; const double *dp;
+    int64_t ni, nd;
+} Dr;
+
+static void dr_init(Dr *d, const OrcDraws *s, int64_t local, int64_t env_id) {
+    d->mode = s->mode; d->have = 0; d->ni = d->nd = 0;
+    d->key[0] = (uint32_t)s->seed; d->key[1] = (uint32_t)(s->seed >> 32);
+    d->ctr[0] = 0; d->ctr[1] = s->epoch; d->ctr[2] = (uint32_t)env_id; d->ctr[3] = (uint32_t)((uint64_t)env_id >> 32);
+    d->ip = s->ints ? s->ints + local * s->int_stride : NULL;
+    d->dp = s->dbls ? s->dbls + local * s->dbl_stride : NULL;
+}
+static void dr_done(const Dr *d, const OrcDraws *s, int64_t local) {
+    if (s->used) { s->used[2 * local] = d->ni; s->used[2 * local + 1] = d->nd; }
+}
+static inline uint32_t dr_u32(Dr *d) { /* philox only: x,y,z,w of block 0, then block 1, ... */
+    if (!d->have) { orc_philox4x32_10(d->ctr, d->key, d->buf); d->ctr[0]++; d->have = 4; }
+    d->ni++;
+    return d->buf[4 - d->have--];
+}
+/* uniform integer in [lo, lo+n): random.randint(lo, lo+n-1) */
+static inline int dr_randint(Dr *d, int lo, int n) {
+    if (d->mode == ORC_REPLAY) { d->ni++; return *d->ip++; }
+    return lo + (int)(((uint64_t)dr_u32(d) * (uint32_t)n) >> 32);
+}
+static inline double dr_dbl(Dr *d) { d->nd++; return *d->dp++; }
+static inline uint32_t thr31(double p) { /* smallest T with (r31 < T) <=> (r31 / 2^31 < p) */
+    double t = ceil(p * 2147483648.0);
+    if (!(t > 0)) return 0;
+    if (t > 2147483648.0) t = 2147483648.0;
+    return (uint32_t)t;
+}
+
+/* next = (r31 < T): T = ceil(P * 2^31); predictor k chosen iff r31 < ceil(cum_k / CODsum * 2^31) and no earlier one was */
+void orc_fill_thresholds(OrcNet *net) {
+    if (net->kind == ORC_TT) {
+        for (int q = 0; q < net->tt_tab_off[net->n]; q++) net->tt_thr[q] = thr31(net->tt_prob[q]);
+    } else {
+        for (int i = 0; i < net->n; i++)
+            for (int q = net->pr_off[i]; q < net->pr_off[i + 1]; q++) net->pr_thr[q] = thr31(net->pr_cum[q] / net->pr_codsum[i]);
+    }
+}
+
+/* geometric gap, PHILOX mode only: number of failures before the next success of a Bernoulli(p) process.
+   u = ((r>>9)+0.5)/2^23 in (0,1);  G = trunc(log2(u) * inv), inv = 1/log2(1-p).
+   log2 is a fixed polynomial evaluated with IEEE single fma only, so CPU and GPU agree bit for bit. */
+static inline float orc_log2f_poly(float x) { /* x > 0, normal */
+    uint32_t b; memcpy(&b, &x, 4);
+    int e = (int)(b >> 23) - 127;
+    b = (b & 0x007FFFFFu) | 0x3F800000u;
+    float m; memcpy(&m, &b, 4);
+    if (m > 1.41421356f) { m *= 0.5f; e += 1; }
+    float t = m - 1.0f; /* in [-0.2929, 0.4142] */
+    /* log2(1+t) = t * P(t); P = degree-7 Chebyshev-node interpolant on [1/sqrt2-1, sqrt2-1], |err| < 1.3e-7 */
+    float p = -1.427597404e-01f;
+    p = fmaf(p, t, 2.326525748e-01f);
+    p = fmaf(p, t, -2.492718250e-01f);
+    p = fmaf(p, t, 2.872888744e-01f);
+    p = fmaf(p, t, -3.602251709e-01f);
+    p = fmaf(p, t, 4.809167087e-01f);
+    p = fmaf(p, t, -7.213529348e-01f);
+    p = fmaf(p, t, 1.442695022e+00f);
+    return fmaf(p, t, (float)e);
+}
+uint32_t orc_geom(uint32_t r, float inv) {
+    float u = ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    float g = orc_log2f_poly(u) * inv;
+    if (!(g < 1.0e9f)) return 1000000000u;
+    return (uint32_t)g;
+}
+float orc_geom_inv(double p) { /* host helper shared by tests: 1/log2(1-p) as float */
+    if (p <= 0) return -1.0f;  /* sentinel: flips disabled */
+    if (p >= 1) return 0.0f;
+    return (float)(1.0 / log2(1.0 - p));
+}
+
+/* ------------------------------------------------------------------------------------ node updates */
+/* common/node.py:31-38 + common/pbn.py:88-92 (PBN.step) / common/pbcn.py:51-66 (PBCN.step) */
+static inline int tt_next_value(const OrcNet *net, const uint8_t *st, int i, Dr *d) {
+    int idx = 0;
+    for (int q = net->tt_in_off[i]; q < net->tt_in_off[i + 1]; q++) idx = (idx << 1) | st[net->tt_in[q]];
+    double p = net->tt_prob[net->tt_tab_off[i] + idx];
+    if (d->mode == ORC_REPLAY) return dr_dbl(d) < p; /* u < p, node.py:37-38 */
+    return (dr_u32(d) >> 1) < net->tt_thr[net->tt_tab_off[i] + idx];
+}
+/* bittner/base.py:89-119 Node.Predstep */
+static inline int pred_next_value(const OrcNet *net, const uint8_t *st, int i, Dr *d) {
+    int q0 = net->pr_off[i], q1 = net->pr_off[i + 1], q = q1 - 1; /* falls through to the LAST predictor, base.py:95-97 */
+    double S = net->pr_codsum[i];
+    if (d->mode == ORC_REPLAY) {
+        double r = dr_dbl(d) * S; /* base.py:94 */
+        for (int k = q0; k < q1; k++) if (net->pr_cum[k] > r) { q = k; break; }
+    } else {
+        uint32_t r = dr_u32(d) >> 1;
+        for (int k = q0; k < q1 - 1; k++) if (r < net->pr_thr[k]) { q = k; break; }
+    }
+    const int32_t *in = net->pr_in + 4 * q;
+    int idx = (st[in[0]] << 3) | (st[in[1]] << 2) | (st[in[2]] << 1) | st[in[3]];
+    return (net->pr_lut[q] >> idx) & 1;
+}
+/* one asynchronous update: PBN.step common/pbn.py:88-92, Graph.step base.py:306-312 */
+static inline void micro_step(const OrcNet *net, uint8_t *st, Dr *d) {
+    int i = dr_randint(d, net->first, net->n - net->first);
+    st[i] = (uint8_t)(net->kind == ORC_TT ? tt_next_value(net, st, i, d) : pred_next_value(net, st, i, d));
+}
+/* Graph.synch_step with perturbations off, base.py:300-303: every node from the OLD state, node order */
+static inline void sync_step(const OrcNet *net, uint8_t *st, uint8_t *tmp, Dr *d) {
+    for (int i = 0; i < net->n; i++)
+        tmp[i] = (uint8_t)(net->kind == ORC_TT ? tt_next_value(net, st, i, d) : pred_next_value(net, st, i, d));
+    memcpy(st, tmp, (size_t)net->n);
+}
+
+/* K1: `steps` updates for B envs; state is uint8 [B][n] */
+int orc_rollout(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, int64_t steps, int sync, const OrcDraws *dr) {
+#pragma omp parallel for schedule(static) if (B >= 256)
+    for (int64_t e = 0; e < B; e++) {
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        uint8_t *st = state + e * net->n;
+        uint8_t *tmp = sync ? (uint8_t *)malloc((size_t)net->n) : NULL;
+        for (int64_t t = 0; t < steps; t++) { if (sync) sync_step(net, st, tmp, &d); else micro_step(net, st, &d); }
+        free(tmp);
+        dr_done(&d, dr, e);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ cube matching */
+static inline int cube_match(const int8_t *cube, const uint8_t *st, int n) {
+    for (int i = 0; i < n; i++) if (cube[i] != 2 && cube[i] != (int8_t)st[i]) return 0;
+    return 1;
+}
+/* Bittner7.is_attracting_state pbn_target.py:562-574 (any cube of any attractor); the multi env's
+   set lookup over expanded wildcards (pbn_target_multi.py:438-454,489-492) accepts the same states */
+static inline int is_attracting(const OrcEnv *env, const uint8_t *st, int n) {
+    if (env->n_att == 0) return 1; /* all-attracting fixture: every state attracting (PBNEnv.is_attracting_state ≡ True, pbn_env.py:19-21) */
+    for (int c = 0; c < env->att_off[env->n_att]; c++) if (cube_match(env->cube + (int64_t)c * n, st, n)) return 1;
+    return 0;
+}
+/* PBNTargetEnv.in_target pbn_target.py:289-301: any cube of the target attractor */
+static inline int in_target_any(const OrcEnv *env, const uint8_t *st, int n, int a) {
+    for (int c = env->att_off[a]; c < env->att_off[a + 1]; c++) if (cube_match(env->cube + (int64_t)c * n, st, n)) return 1;
+    return 0;
+}
+/* PBNTargetMultiEnv.in_target pbn_target_multi.py:190-199: returns False at the FIRST mismatch of the FIRST cube (Q12) */
+static inline int in_target_first(const OrcEnv *env, const uint8_t *st, int n, int a) {
+    if (env->att_off[a] == env->att_off[a + 1]) return 0;
+    return cube_match(env->cube + (int64_t)env->att_off[a] * n, st, n);
+}
+static inline int in_target_set(const OrcEnv *env, const uint8_t *st, int n) { /* tuple(obs) in self.target_nodes, pbn_env.py:168 */
+    for (int c = env->tgt_first; c < env->tgt_first + env->n_tgt; c++) if (cube_match(env->cube + (int64_t)c * n, st, n)) return 1;
+    return 0;
+}
+/* PBCNEnv._get_reward pbcn_env.py:52-65 */
+static inline int pbcn_reward(const OrcEnv *env, const uint8_t *st, int n, int *term) {
+    if (in_target_set(env, st, n)) { *term = 1; return env->successful_reward; }
+    int m = 0;
+    for (int a = 0; a < env->n_att; a++) m += in_target_any(env, st, n, a);
+    *term = 0;
+    return -env->wrong_attractor_cost * m;
+}
+
+/* K2: one env.step for B envs.
+   actions: int32 [B][K].  PBN/PBCN/TARGET: K=1.  MULTI: K actions (value <0 = absent slot).
+   PBN_SD: K=2 (primitive action, interval).  PBCN_SD: K = 1 + n_control (interval, control bits).
+   outputs: reward int32[B], term/trunc uint8[B], inner int32[B] (micro-steps executed), obs uint8[B][n]
+   (obs differs from state only for MULTI's pre-update capture, Q11). */
+int orc_env_step(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, const int32_t *target_att,
+                 const int32_t *actions, int K, uint8_t *obs, int32_t *reward, uint8_t *term, uint8_t *trunc,
+                 int32_t *inner, int64_t B, int64_t env0, const OrcDraws *dr) {
+    const int n = net->n;
+#pragma omp parallel for schedule(dynamic, 64) if (B >= 256)
+    for (int64_t e = 0; e < B; e++) {
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        uint8_t *st = state + e * n, *ob = obs + e * n;
+        const int32_t *act = actions + e * K;
+        int rew = 0, tm = 0, tr = 0, in = 0;
+        switch (env->kind) {
+        case ORC_ENV_PBN: { /* pbn_env.py:141-154, reward :171-183 */
+            int a = act[0];
+            if (a != 0) st[a] ^= 1; /* flips index `action` itself, Q3 */
+            micro_step(net, st, &d); in = 1; /* is_attracting_state ≡ True: the while never iterates */
+            if (in_target_set(env, st, n)) { rew = 20; tm = 1; } else rew = -4 - (a != 0);
+            memcpy(ob, st, (size_t)n);
+        } break;
+        case ORC_ENV_PBCN: { /* pbcn_env.py:67-80 */
+            int a = act[0];
+            if (a != 0) st[a] ^= 1;
+            micro_step(net, st, &d); in = 1;
+            rew = pbcn_reward(env, st, n, &tm);
+            memcpy(ob, st, (size_t)n);
+        } break;
+        case ORC_ENV_TARGET: { /* pbn_target.py:261-280, reward :303-326 */
+            int a = act[0];
+            n_steps[e] += 1;
+            if (a != 0) st[a - 1] ^= 1;
+            micro_step(net, st, &d); in = 1;
+            while (!env->force && !is_attracting(env, st, n) && in < env->max_inner) { micro_step(net, st, &d); in++; }
+            if (in_target_any(env, st, n, target_att[e])) { rew = 20; tm = 1; } else rew = -5;
+            tr = (n_steps[e] == env->horizon);
+            memcpy(ob, st, (size_t)n);
+        } break;
+        case ORC_ENV_MULTI: { /* pbn_target_multi.py:119-154, reward :201-225 */
+            int cnt = 0;
+            n_steps[e] += 1;
+            for (int k = 0; k < K; k++) {
+                int a = act[k];
+                if (a < 0) continue;
+                if (env->dedup) { int dup = 0; for (int j = 0; j < k; j++) dup |= (act[j] == a); if (dup) continue; }
+                cnt++;
+                if (a != 0) st[a - 1] ^= 1;
+            }
+            memcpy(ob, st, (size_t)n);  /* observation captured BEFORE the update, :133 */
+            micro_step(net, st, &d); in = 1;
+            while (!is_attracting(env, ob, n) && in < env->max_inner) { micro_step(net, st, &d); memcpy(ob, st, (size_t)n); in++; }
+            if (in_target_first(env, ob, n, target_att[e])) { rew = 1000; tm = 1; }
+            rew -= cnt;
+            tr = (n_steps[e] == env->horizon);
+        } break;
+        case ORC_ENV_PBN_SD: { /* sampled_data.py:52-88 */
+            int a = act[0], interval = act[1];
+            for (int i = 0; i < interval; i++) {
+                if (a != 0) st[a - 1] ^= 1;
+                micro_step(net, st, &d); in++;
+                if (in_target_set(env, st, n)) { rew += 20; tm = 1; } else { rew += -4 - (a != 0); tm = 0; }
+            }
+            memcpy(ob, st, (size_t)n);
+        } break;
+        case ORC_ENV_PBCN_SD: { /* sampled_data.py:139-189 */
+            int interval = act[0], tstep = -1;
+            for (int i = 0; i < interval; i++) {
+                if (env->control_write) for (int c = 0; c < env->n_control; c++) st[c] = (uint8_t)(act[1 + c] != 0);
+                micro_step(net, st, &d); in++;
+                int r = pbcn_reward(env, st, n, &tm) - 1; /* time_step_cost = 1 */
+                if (tstep >= 0) r -= env->successful_reward; /* overshoot penalty */
+                else if (tm) tstep = i;
+                rew += r;
+            }
+            memcpy(ob, st, (size_t)n);
+        } break;
+        default: break;
+        }
+        reward[e] = rew; term[e] = (uint8_t)tm; trunc[e] = (uint8_t)tr; inner[e] = in;
+        dr_done(&d, dr, e);
+    }
+    return 0;
+}
+
+/* reset for the envs selected by mask (NULL = all).
+   TARGET: pbn_target.py:328-352 — sample(all_attractors, 2) -> choice(state cube), choice(target cube)
+           -> per position: randint(0,1) for a '*' in state, then for a '*' in target.
+   MULTI : pbn_target_multi.py:227-259 — state attractor = first, target = last (Q14), rest identical.
+   PBN/PBCN family: pbn_env.py:190-213 — attractor with <= 10 states, uniform state from it, PBN.reset forces
+           state[0]=0 (common/pbn.py:77).  The reference's discarded first choice() is not drawn in PHILOX mode;
+           in REPLAY mode the recorded indices are (attractor index tries..., state index). */
+int orc_env_reset(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, int32_t *target_att,
+                  uint8_t *target_state, const uint8_t *mask, int64_t B, int64_t env0, const OrcDraws *dr) {
+    const int n = net->n;
+    for (int64_t e = 0; e < B; e++) {
+        if (mask && !mask[e]) continue;
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        uint8_t *st = state + e * n;
+        if (env->kind == ORC_ENV_TARGET || env->kind == ORC_ENV_MULTI) {
+            int A = env->n_att, a, b;
+            if (env->kind == ORC_ENV_TARGET) {
+                if (d.mode == ORC_REPLAY) { a = dr_randint(&d, 0, A); b = dr_randint(&d, 0, A); }
+                else { a = dr_randint(&d, 0, A); b = dr_randint(&d, 0, A - 1); if (b >= a) b++; }
+            } else { a = 0; b = A - 1; }
+            int cs = env->att_off[a] + dr_randint(&d, 0, env->att_off[a + 1] - env->att_off[a]);
+            int ct = env->att_off[b] + dr_randint(&d, 0, env->att_off[b + 1] - env->att_off[b]);
+            const int8_t *s = env->cube + (int64_t)cs * n, *t = env->cube + (int64_t)ct * n;
+            for (int i = 0; i < n; i++) {
+                st[i] = (uint8_t)(s[i] == 2 ? dr_randint(&d, 0, 2) : s[i]);
+                uint8_t tv = (uint8_t)(t[i] == 2 ? dr_randint(&d, 0, 2) : t[i]);
+                if (target_state) target_state[e * n + i] = tv;
+            }
+            target_att[e] = b;
+            n_steps[e] = 0;
+        } else {
+            int a;
+            do { a = dr_randint(&d, 0, env->n_att); } while (env->att_off[a + 1] - env->att_off[a] > 10);
+            int c = env->att_off[a] + dr_randint(&d, 0, env->att_off[a + 1] - env->att_off[a]);
+            for (int i = 0; i < n; i++) st[i] = (uint8_t)env->cube[(int64_t)c * n + i];
+            st[0] = 0;
+            if (n_steps) n_steps[e] = 0;
+        }
+        dr_done(&d, dr, e);
+    }
+    return 0;
+}
+
+/* Graph.genRandState base.py:368-370: randint(0,1) per node */
+int orc_rand_state(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, const OrcDraws *dr) {
+    for (int64_t e = 0; e < B; e++) {
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        for (int i = 0; i < net->n; i++) state[e * net->n + i] = (uint8_t)dr_randint(&d, 0, 2);
+        dr_done(&d, dr, e);
+    }
+    return 0;
+}
+
+/* K3: utils/eval.py:76-103 _ssd_run for `chains` chains x `iters` iterations, model=None.
+   Per iteration: hist[bucket(state)] += 1 (before stepping, :88-89); flip each node w.p. p (:92-95);
+   env.step(0) (:96) = PBNTargetEnv.step: one update, then until attracting (cap max_inner).
+   REPLAY: n doubles per iteration then the step's draws.  PHILOX: flips are a geometric-skip Bernoulli
+   process over the linear index (iteration*n + node) — the same law as n independent Bernoulli(p) per
+   iteration, using 1+#flips draws instead of n.
+   bucket = target-node bits MSB-first (pbn_target.py:383-391).  hist is uint64 [2^g], summed over chains. */
+int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains, int64_t env0, int64_t iters,
+            double p, const int32_t *tgt_nodes, int g, uint64_t *hist, const OrcDraws *dr) {
+    const int n = net->n;
+    const int64_t nb = (int64_t)1 << g;
+    const float inv = orc_geom_inv(p);
+    int nthreads = 1;
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void); extern int omp_get_thread_num(void);
+    nthreads = omp_get_max_threads();
+#endif
+    uint64_t *priv = (uint64_t *)calloc((size_t)(nthreads * nb), sizeof(uint64_t));
+#pragma omp parallel for schedule(static) if (chains >= 256)
+    for (int64_t e = 0; e < chains; e++) {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        uint64_t *h = priv + (int64_t)tid * nb;
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        uint8_t *st = state + e * n;
+        int64_t pos = 0;
+        if (d.mode == ORC_PHILOX) pos = inv < 0 ? INT64_MAX / 2 : (int64_t)orc_geom(dr_u32(&d), inv);
+        for (int64_t t = 0; t < iters; t++) {
+            int64_t b = 0;
+            for (int k = 0; k < g; k++) b = (b << 1) | st[tgt_nodes[k]];
+            h[b]++;
+            if (d.mode == ORC_REPLAY) {
+                for (int j = 0; j < n; j++) if (dr_dbl(&d) < p) st[j] ^= 1; /* graph.flipNode(j), eval.py:92-95 */
+            } else {
+                while (pos < n) { st[pos] ^= 1; pos += 1 + (int64_t)orc_geom(dr_u32(&d), inv); }
+                pos -= n;
+            }
+            micro_step(net, st, &d);
+            int in = 1;
+            while (env && !env->force && !is_attracting(env, st, n) && in < env->max_inner) { micro_step(net, st, &d); in++; }
+        }
+        dr_done(&d, dr, e);
+    }
+    for (int t = 0; t < nthreads; t++) for (int64_t b = 0; b < nb; b++) hist[b] += priv[t * nb + b];
+    free(priv);
+    return 0;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,144 @@
+"""CPU: the C oracle (oracle/pbn_oracle.c) replayed against golden vectors recorded from the
+unmodified reference (oracle/make_golden.py).  Bit-exact: states, observations, rewards, flags,
+and the number of draws consumed."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from golden_util import Traj, cubes_to_attractors, load, pbn_data_from
+
+
+def _rd(ints, dbls):
+    return orc.Draws(ints=np.asarray(ints, np.int32).reshape(1, -1) if len(ints) else np.zeros((1, 1), np.int32),
+                     dbls=np.asarray(dbls, np.float64).reshape(1, -1) if len(dbls) else np.zeros((1, 1), np.float64))
+
+
+def _check_used(d, ints, dbls):
+    assert tuple(d.used[0]) == (len(ints), len(dbls))
+
+
+def test_philox_kat():
+    # Random123 known-answer vectors for philox4x32-10
+    assert orc.philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert orc.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert orc.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+@pytest.mark.parametrize("name", ["b28_graph_core.npz", "b100_graph_core.npz", "b200_graph_core.npz"])
+def test_graph_core(name):
+    z = load(name)
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    for e in range(int(z["n_traj"])):
+        tr = Traj(z, e)
+        # op 1 = genRandState: randint(0,1) per node
+        ints, dbls = tr.draws(0)
+        d = _rd(ints, dbls)
+        st = orc.rand_state(net, 1, d)
+        assert np.array_equal(st[0], tr.state[0])
+        for t in range(1, tr.T):
+            ints, dbls = tr.draws(t)
+            d = _rd(ints, dbls)
+            if tr.op[t] == 0:
+                a = int(tr.act[t, 0])
+                if a >= 0:
+                    st[0, a] ^= 1  # Graph.flipNode
+                orc.rollout(net, st, 1, d)
+            else:
+                orc.rollout(net, st, 1, d, sync=True)
+            _check_used(d, ints, dbls)
+            assert np.array_equal(st[0], tr.state[t]), (name, e, t)
+
+
+def test_tt_core():
+    z = load("tt40_core.npz")
+    net = orc.net_from_pbn_data(pbn_data_from(z))
+    tr = Traj(z, 0)
+    st = tr.state[0:1].copy()
+    for t in range(1, tr.T):
+        ints, dbls = tr.draws(t)
+        d = _rd(ints, dbls)
+        a = int(tr.act[t, 0])
+        if a >= 0:
+            st[0, a] ^= 1  # PBN.flip
+        orc.rollout(net, st, 1, d)
+        _check_used(d, ints, dbls)
+        assert np.array_equal(st[0], tr.state[t]), t
+
+
+def _run_env_trace(net, env, tr, K, reset_kind=True):
+    n = net.n
+    st = np.zeros((1, n), np.uint8)
+    n_steps = np.zeros(1, np.int32)
+    tatt = np.zeros(1, np.int32)
+    for t in range(tr.T):
+        ints, dbls = tr.draws(t)
+        d = _rd(ints, dbls)
+        if tr.op[t] == 1:
+            orc.env_reset(net, env, st, n_steps, tatt, d)
+            _check_used(d, ints, dbls)
+            assert np.array_equal(st[0], tr.state[t]), ("reset", t)
+            if tr.target_att[t] >= 0:
+                assert tatt[0] == tr.target_att[t]
+        else:
+            obs, rew, term, trunc, inner = orc.env_step(net, env, st, n_steps, tatt, tr.act[t:t + 1, :K], d)
+            _check_used(d, ints, dbls)
+            assert np.array_equal(st[0], tr.state[t]), ("state", t)
+            assert np.array_equal(obs[0], tr.obs[t]), ("obs", t)
+            assert (rew[0], term[0], trunc[0]) == (tr.reward[t], tr.term[t], tr.trunc[t]), ("reward", t)
+
+
+def test_pbn_env_ex5():
+    z = load("ex5_pbnenv.npz")
+    net = orc.net_from_pbn_data(pbn_data_from(z))
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = orc.Env(orc.ENV_PBN, 5, attractors=atts, targets=[tuple(t) for t in z["targets"]])
+    for e in range(int(z["n_traj"])):
+        _run_env_trace(net, env, Traj(z, e), 1)
+
+
+def test_pbcn_and_sampled_data_ex5():
+    z = load("ex5_pbcn_sampled.npz")
+    net = orc.net_from_pbn_data(pbn_data_from(z))
+    kinds = [orc.ENV_PBCN, orc.ENV_PBCN_SD, orc.ENV_PBN_SD]
+    for e, kind in enumerate(kinds):
+        atts = cubes_to_attractors(z[f"e{e}/att_cubes"], z[f"e{e}/att_off"])
+        env = orc.Env(kind, 5, attractors=atts, targets=[tuple(t) for t in z["targets"]],
+                      n_control=int(z[f"e{e}/M"]), successful_reward=int(z[f"e{e}/successful_reward"]),
+                      wrong_attractor_cost=int(z[f"e{e}/wrong_attractor_cost"]))
+        _run_env_trace(net, env, Traj(z, e), 1 if e == 0 else 2)
+
+
+def test_target_env_b28():
+    z = load("b28_target_env.npz")
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    for e in range(int(z["n_traj"])):
+        env = orc.Env(orc.ENV_TARGET, net.n, attractors=atts, horizon=int(z["horizon"]), max_inner=int(z["cap"]),
+                      force=int(z[f"e{e}/force"]))
+        _run_env_trace(net, env, Traj(z, e), 1)
+
+
+def test_multi_env_b28():
+    z = load("b28_multi_env.npz")
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    for e in range(int(z["n_traj"])):
+        env = orc.Env(orc.ENV_MULTI, net.n, attractors=atts, horizon=int(z["horizon"]), max_inner=int(z["cap"]),
+                      dedup=int(z[f"e{e}/dedup"]))
+        _run_env_trace(net, env, Traj(z, e), 3)
+
+
+def test_ssd_replay_b100():
+    z = load("b100_ssd_replay.npz")
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    env = orc.Env(orc.ENV_TARGET, net.n)  # all-attracting fixture: one update per iteration
+    st = z["init"].copy()
+    d = orc.Draws(ints=z["ints"], dbls=z["dbls"])
+    hist = orc.ssd(net, env, st, int(z["iters"]), float(z["p"]), z["tgt_nodes"], d)
+    assert np.array_equal(hist.astype(np.int64), z["hist"].sum(0))
+    assert np.array_equal(d.used[:, 0], [z["ints"].shape[1]] * 2) and np.array_equal(d.used[:, 1], [z["dbls"].shape[1]] * 2)
