@@ -1,0 +1,760 @@
+// pbn_b200.cu — sm_100a kernels and the C-ABI of libpbn_b200.so (see include/pbn_b200.h).
+//
+// Thread-per-env kernels; the packed network image and the cube tables are staged once per block into
+// shared memory, each env's bit-packed state lives in a shared-memory column for the whole launch, so a
+// rollout / SSD launch touches HBM only for 2*W32 words per env plus the histogram.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbn_device.cuh"
+
+#define PBN_BLOCK 256
+
+// ----------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(PBN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+extern "C" const char *pbn_last_error(void) { return g_err.c_str(); }
+extern "C" const char *pbn_version(void) { return "pbn_b200 0.1 (sm_100a)"; }
+
+// ----------------------------------------------------------------------------------------------- handles
+struct PbnNet {
+    NetView v;
+    std::vector<void *> owned;
+};
+struct PbnEnv {
+    EnvView v;
+    const PbnNet *net;
+    std::vector<void *> owned;
+};
+
+template <class T>
+static int upload(std::vector<void *> &owned, const T *host, size_t count, const T **dev) {
+    void *p = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    owned.push_back(p);
+    if (count) CK(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T *>(p);
+    return PBN_OK;
+}
+
+static inline u32 thr31(double p) {  // smallest T with (r31 < T) <=> (r31 / 2^31 < p)
+    double t = std::ceil(p * 2147483648.0);
+    if (!(t > 0)) return 0;
+    if (t > 2147483648.0) t = 2147483648.0;
+    return (u32)t;
+}
+
+// Network compiler back end (host): reference-form tables -> packed image.
+extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
+    if (!d || !out) return fail(PBN_ERR_ARG, "null argument");
+    const int n = d->n_nodes;
+    if (n < 1) return fail(PBN_ERR_ARG, "n_nodes < 1");
+    if (d->first_updatable < 0 || d->first_updatable >= n) return fail(PBN_ERR_ARG, "first_updatable out of range");
+    PbnNet *net = new PbnNet();
+    NetView &v = net->v;
+    memset(&v, 0, sizeof v);
+    v.kind = d->kind; v.n = n; v.first = d->first_updatable; v.w32 = (n + 31) / 32;
+    std::vector<unsigned char> blob;
+    int rc = PBN_OK;
+    if (d->kind == PBN_NET_PRED) {
+        if (n > 256) { delete net; return fail(PBN_ERR_UNSUPPORTED, "predictor networks support at most 256 nodes"); }
+        int fmax = 0;
+        for (int i = 0; i < n; i++) {
+            int f = d->pr_off[i + 1] - d->pr_off[i];
+            if (f < 1) { delete net; return fail(PBN_ERR_ARG, "node without predictors"); }
+            fmax = f > fmax ? f : fmax;
+        }
+        const int ts = ((fmax - 1 + 3) / 4) * 4 > 0 ? ((fmax - 1 + 3) / 4) * 4 : 4;
+        v.fmax = fmax; v.ts = ts;
+        v.off_thr = 0;
+        v.off_rec = n * ts * 4;
+        blob.resize((size_t)v.off_rec + (size_t)n * fmax * 8);
+        u32 *thr = reinterpret_cast<u32 *>(blob.data());
+        uint2 *rec = reinterpret_cast<uint2 *>(blob.data() + v.off_rec);
+        for (int i = 0; i < n; i++) {
+            const int q0 = d->pr_off[i], f = d->pr_off[i + 1] - q0;
+            for (int k = 0; k < ts; k++)
+                thr[i * ts + k] = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
+            for (int k = 0; k < fmax; k++) {
+                const int q = q0 + (k < f ? k : f - 1);
+                u32 packed = 0;
+                for (int j = 0; j < 4; j++) {
+                    int idx = d->pr_in[4 * q + j];
+                    if (idx < 0 || idx >= n) { delete net; return fail(PBN_ERR_ARG, "predictor input out of range"); }
+                    packed |= (u32)idx << (8 * j);
+                }
+                rec[i * fmax + k] = make_uint2(packed, d->pr_lut[q]);
+            }
+        }
+        const int np = d->pr_off[n];
+        rc |= upload(net->owned, d->pr_off, (size_t)n + 1, &v.pr_off);
+        rc |= upload(net->owned, d->pr_cum, (size_t)np, &v.pr_cum);
+        rc |= upload(net->owned, d->pr_codsum, (size_t)n, &v.pr_codsum);
+    } else if (d->kind == PBN_NET_TT) {
+        if (n > 65536) { delete net; return fail(PBN_ERR_UNSUPPORTED, "truth-table networks support at most 65536 nodes"); }
+        const int nin = d->tt_in_off[n], ntab = d->tt_tab_off[n];
+        if (nin > 65535) { delete net; return fail(PBN_ERR_UNSUPPORTED, "too many inputs in total"); }
+        v.off_node = 0;
+        v.off_in = n * 8;
+        v.off_thr = (v.off_in + nin * 2 + 15) & ~15;
+        blob.resize((size_t)v.off_thr + (size_t)ntab * 4);
+        uint2 *node = reinterpret_cast<uint2 *>(blob.data());
+        unsigned short *in = reinterpret_cast<unsigned short *>(blob.data() + v.off_in);
+        u32 *thr = reinterpret_cast<u32 *>(blob.data() + v.off_thr);
+        for (int i = 0; i < n; i++) {
+            const int k = d->tt_in_off[i + 1] - d->tt_in_off[i];
+            if (k < 0 || k > 16 || d->tt_tab_off[i + 1] - d->tt_tab_off[i] != (1 << k)) {
+                delete net;
+                return fail(PBN_ERR_ARG, "truth table size does not match its input count (k <= 16)");
+            }
+            node[i] = make_uint2((u32)d->tt_tab_off[i], (u32)d->tt_in_off[i] | ((u32)k << 16));
+        }
+        for (int q = 0; q < nin; q++) {
+            if (d->tt_in[q] < 0 || d->tt_in[q] >= n) { delete net; return fail(PBN_ERR_ARG, "input index out of range"); }
+            in[q] = (unsigned short)d->tt_in[q];
+        }
+        for (int q = 0; q < ntab; q++) thr[q] = thr31(d->tt_prob[q]);
+        rc |= upload(net->owned, d->tt_prob, (size_t)ntab, &v.tt_prob);
+    } else {
+        delete net;
+        return fail(PBN_ERR_ARG, "unknown network kind");
+    }
+    blob.resize((blob.size() + 15) & ~(size_t)15);
+    v.blob_bytes = (int)blob.size();
+    rc |= upload(net->owned, blob.data(), blob.size(), &v.blob);
+    if (rc) { pbn_net_destroy(net); return PBN_ERR_CUDA; }
+    if (v.blob_bytes > 160 * 1024) { pbn_net_destroy(net); return fail(PBN_ERR_UNSUPPORTED, "network image exceeds shared memory"); }
+    *out = net;
+    return PBN_OK;
+}
+
+extern "C" int pbn_net_destroy(PbnNet *net) {
+    if (!net) return PBN_OK;
+    for (void *p : net->owned) cudaFree(p);
+    delete net;
+    return PBN_OK;
+}
+extern "C" int pbn_net_words(const PbnNet *net) { return net ? net->v.w32 : 0; }
+
+extern "C" int pbn_env_create(const PbnNet *net, const PbnEnvDesc *d, PbnEnv **out) {
+    if (!net || !d || !out) return fail(PBN_ERR_ARG, "null argument");
+    if (d->kind < PBN_ENV_PBN || d->kind > PBN_ENV_PBCN_SD) return fail(PBN_ERR_ARG, "unknown env kind");
+    const int n = net->v.n, w32 = net->v.w32;
+    PbnEnv *env = new PbnEnv();
+    env->net = net;
+    EnvView &v = env->v;
+    memset(&v, 0, sizeof v);
+    v.kind = d->kind; v.horizon = d->horizon; v.max_inner = d->max_inner > 0 ? d->max_inner : 1;
+    v.force = d->force; v.dedup = d->dedup; v.control_write = d->control_write; v.n_control = d->n_control;
+    v.successful_reward = d->successful_reward; v.wrong_attractor_cost = d->wrong_attractor_cost;
+    v.n_att = d->n_att; v.tgt_first = d->tgt_first; v.n_tgt = d->n_tgt;
+    const int n_att_cubes = d->n_att > 0 ? d->att_off[d->n_att] : 0;
+    v.n_cubes = n_att_cubes > d->tgt_first + d->n_tgt ? n_att_cubes : d->tgt_first + d->n_tgt;
+    if (d->n_tgt == 0) v.n_cubes = n_att_cubes;
+    v.off_cubes = ((d->n_att + 1) * 4 + 15) & ~15;
+    std::vector<unsigned char> img((size_t)v.off_cubes + (size_t)v.n_cubes * w32 * 8 + 16, 0);
+    int *off = reinterpret_cast<int *>(img.data());
+    for (int a = 0; a <= d->n_att; a++) off[a] = d->n_att > 0 ? d->att_off[a] : 0;
+    u32 *cw = reinterpret_cast<u32 *>(img.data() + v.off_cubes);
+    for (int c = 0; c < v.n_cubes; c++)
+        for (int i = 0; i < n; i++) {
+            int8_t x = d->cube[(size_t)c * n + i];
+            if (x == 0 || x == 1) {
+                cw[((size_t)c * w32 + (i >> 5)) * 2] |= 1u << (i & 31);
+                if (x) cw[((size_t)c * w32 + (i >> 5)) * 2 + 1] |= 1u << (i & 31);
+            } else if (x != 2) {
+                delete env;
+                return fail(PBN_ERR_ARG, "cube entries must be 0, 1 or 2 ('*')");
+            }
+        }
+    img.resize((img.size() + 15) & ~(size_t)15);
+    v.img_bytes = (int)img.size();
+    if (v.img_bytes + net->v.blob_bytes > 190 * 1024) { delete env; return fail(PBN_ERR_UNSUPPORTED, "cube tables exceed shared memory"); }
+    if (upload(env->owned, img.data(), img.size(), &v.img)) { pbn_env_destroy(env); return PBN_ERR_CUDA; }
+    *out = env;
+    return PBN_OK;
+}
+extern "C" int pbn_env_destroy(PbnEnv *env) {
+    if (!env) return PBN_OK;
+    for (void *p : env->owned) cudaFree(p);
+    delete env;
+    return PBN_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- kernel helpers
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__device__ __forceinline__ void stage(unsigned char *dst, const unsigned char *src, int bytes) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) d[i] = s[i];
+}
+__device__ __forceinline__ void load_state(const Col &c, const u32 *g, long long B, long long e, int w32) {
+    for (int w = 0; w < w32; w++) c.set_word(w, g[(long long)w * B + e]);
+}
+__device__ __forceinline__ void store_state(const Col &c, u32 *g, long long B, long long e, int w32) {
+    for (int w = 0; w < w32; w++) g[(long long)w * B + e] = c.word(w);
+}
+
+static DrawView make_draws(const PbnDraws *d) {
+    DrawView v;
+    v.mode = d->mode; v.epoch = d->epoch;
+    v.seed_lo = (u32)d->seed; v.seed_hi = (u32)(d->seed >> 32);
+    v.ints = d->ints; v.dbls = d->dbls;
+    v.int_stride = d->int_stride; v.dbl_stride = d->dbl_stride;
+    v.used = (long long *)d->used;
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------------- K1 rollout
+template <int NET, int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, u32 *state, long long B, long long env0,
+                                                       long long steps, int sync) {
+    unsigned char *blob = smem_raw;
+    u32 *sst = reinterpret_cast<u32 *>(smem_raw + nv.blob_bytes);
+    stage(blob, nv.blob, nv.blob_bytes);
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Col st{sst + threadIdx.x, (int)blockDim.x};
+    Col tmp{sst + nv.w32 * blockDim.x + threadIdx.x, (int)blockDim.x};
+    if (e < B) load_state(st, state, B, e, nv.w32);
+    __syncthreads();
+    if (e >= B) return;
+    Draw<MODE> d;
+    d.init(dv, e, env0 + e);
+    if (sync)
+        for (long long t = 0; t < steps; t++) sync_step<NET, MODE>(nv, blob, st, tmp, d);
+    else
+        for (long long t = 0; t < steps; t++) micro_step<NET, MODE>(nv, blob, st, d);
+    store_state(st, state, B, e, nv.w32);
+    d.done(dv, e);
+}
+
+// ----------------------------------------------------------------------------------------------- K2 env step
+__device__ __forceinline__ bool is_attracting(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, int w32) {
+    if (ev.n_att == 0) return true;
+    return match_range(cubes, 0, att_off[ev.n_att], st, w32);
+}
+__device__ __forceinline__ int pbcn_reward(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, int w32,
+                                           int &term) {
+    if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { term = 1; return ev.successful_reward; }
+    int m = 0;
+    for (int a = 0; a < ev.n_att; a++) m += match_range(cubes, att_off[a], att_off[a + 1], st, w32) ? 1 : 0;
+    term = 0;
+    return -ev.wrong_attractor_cost * m;
+}
+
+template <int NET, int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+                                                        const int *target_att, const int *actions, int K, u32 *obs_state,
+                                                        int *reward, unsigned char *terminated, unsigned char *truncated,
+                                                        int *inner_steps, long long B, long long env0) {
+    unsigned char *blob = smem_raw;
+    unsigned char *img = smem_raw + nv.blob_bytes;
+    u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    stage(blob, nv.blob, nv.blob_bytes);
+    stage(img, ev.img, ev.img_bytes);
+    const int *att_off = reinterpret_cast<const int *>(img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w32 = nv.w32;
+    Col st{sst + threadIdx.x, (int)blockDim.x};
+    Col ob{sst + w32 * blockDim.x + threadIdx.x, (int)blockDim.x};
+    if (e < B) load_state(st, state, B, e, w32);
+    __syncthreads();
+    if (e >= B) return;
+    Draw<MODE> d;
+    d.init(dv, e, env0 + e);
+    const int *act = actions + e * K;
+    int rew = 0, tm = 0, tr = 0, in = 0;
+    bool obs_is_state = true;
+    switch (ev.kind) {
+    case PBN_ENV_PBN: {  // pbn_env.py:141-154, reward :171-183
+        int a = act[0];
+        if (a != 0) st.flip(a);  // flips index `action` itself (Q3)
+        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew = 20; tm = 1; }
+        else rew = -4 - (a != 0);
+    } break;
+    case PBN_ENV_PBCN: {  // pbcn_env.py:67-80
+        int a = act[0];
+        if (a != 0) st.flip(a);
+        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        rew = pbcn_reward(ev, att_off, cubes, st, w32, tm);
+    } break;
+    case PBN_ENV_TARGET: {  // pbn_target.py:261-280, reward :303-326
+        int a = act[0];
+        int ns = n_steps[e] + 1;
+        n_steps[e] = ns;
+        if (a != 0) st.flip(a - 1);
+        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        while (!ev.force && in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) {
+            micro_step<NET, MODE>(nv, blob, st, d); in++;
+        }
+        int ta = target_att[e];
+        if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
+        tr = (ns == ev.horizon);
+    } break;
+    case PBN_ENV_MULTI: {  // pbn_target_multi.py:119-154, reward :201-225
+        int cnt = 0;
+        int ns = n_steps[e] + 1;
+        n_steps[e] = ns;
+        for (int k = 0; k < K; k++) {
+            int a = act[k];
+            if (a < 0) continue;
+            if (ev.dedup) {
+                bool dup = false;
+                for (int j = 0; j < k; j++) dup |= (act[j] == a);
+                if (dup) continue;
+            }
+            cnt++;
+            if (a != 0) st.flip(a - 1);
+        }
+        for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
+        obs_is_state = false;
+        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, ob, w32)) {
+            micro_step<NET, MODE>(nv, blob, st, d);
+            for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
+            in++;
+        }
+        int ta = target_att[e];
+        // in_target returns at the first mismatch of the FIRST cube (Q12)
+        if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew = 1000; tm = 1; }
+        rew -= cnt;
+        tr = (ns == ev.horizon);
+    } break;
+    case PBN_ENV_PBN_SD: {  // sampled_data.py:52-88
+        int a = act[0], interval = act[1];
+        for (int i = 0; i < interval; i++) {
+            if (a != 0) st.flip(a - 1);
+            micro_step<NET, MODE>(nv, blob, st, d); in++;
+            if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew += 20; tm = 1; }
+            else { rew += -4 - (a != 0); tm = 0; }
+        }
+    } break;
+    case PBN_ENV_PBCN_SD: {  // sampled_data.py:139-189
+        int interval = act[0], tstep = -1;
+        for (int i = 0; i < interval; i++) {
+            if (ev.control_write)
+                for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
+            micro_step<NET, MODE>(nv, blob, st, d); in++;
+            int r = pbcn_reward(ev, att_off, cubes, st, w32, tm) - 1;  // time_step_cost = 1
+            if (tstep >= 0) r -= ev.successful_reward;                // overshoot penalty
+            else if (tm) tstep = i;
+            rew += r;
+        }
+    } break;
+    default: break;
+    }
+    store_state(st, state, B, e, w32);
+    if (obs_state) store_state(obs_is_state ? st : ob, obs_state, B, e, w32);
+    reward[e] = rew;
+    terminated[e] = (unsigned char)tm;
+    truncated[e] = (unsigned char)tr;
+    if (inner_steps) inner_steps[e] = in;
+    d.done(dv, e);
+}
+
+// ----------------------------------------------------------------------------------------------- reset
+template <int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_env_reset(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+                                                         int *target_att, u32 *target_state, const unsigned char *mask,
+                                                         long long B, long long env0) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B || (mask && !mask[e])) return;
+    const int *att_off = reinterpret_cast<const int *>(ev.img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(ev.img + ev.off_cubes);
+    const int n = nv.n, w32 = nv.w32;
+    Draw<MODE> d;
+    d.init(dv, e, env0 + e);
+    if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
+        const int A = ev.n_att;
+        int a, b;
+        if (ev.kind == PBN_ENV_TARGET) {  // random.sample(all_attractors, 2), pbn_target.py:333
+            if constexpr (MODE == PBN_DRAW_REPLAY) { a = d.randint(0, A); b = d.randint(0, A); }
+            else { a = d.randint(0, A); b = d.randint(0, A - 1); if (b >= a) b++; }
+        } else { a = 0; b = A - 1; }  // first -> last (pbn_target_multi.py:237-238)
+        const int cs = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
+        const int ct = att_off[b] + d.randint(0, att_off[b + 1] - att_off[b]);
+        const u32 *ps = cubes + (size_t)cs * w32 * 2, *pt = cubes + (size_t)ct * w32 * 2;
+        u32 sw = 0, tw = 0;
+        for (int i = 0; i < n; i++) {  // '*' -> randint(0,1), state then target, position by position (:336-340)
+            const int w = i >> 5, bit = i & 31;
+            u32 sv = ((ps[2 * w] >> bit) & 1u) ? ((ps[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
+            u32 tv = ((pt[2 * w] >> bit) & 1u) ? ((pt[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
+            sw |= sv << bit; tw |= tv << bit;
+            if (bit == 31 || i == n - 1) {
+                state[(long long)w * B + e] = sw;
+                if (target_state) target_state[(long long)w * B + e] = tw;
+                sw = tw = 0;
+            }
+        }
+        target_att[e] = b;
+        n_steps[e] = 0;
+    } else {  // pbn_env.py:201-206: an attractor with <= 10 states, a uniform state of it; PBN.reset forces state[0] = 0
+        int a;
+        do { a = d.randint(0, ev.n_att); } while (att_off[a + 1] - att_off[a] > 10);
+        const int c = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
+        const u32 *p = cubes + (size_t)c * w32 * 2;
+        for (int w = 0; w < w32; w++) state[(long long)w * B + e] = (w == 0) ? (p[1] & ~1u) : p[2 * w + 1];
+        if (n_steps) n_steps[e] = 0;
+    }
+    d.done(dv, e);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_rand_state(NetView nv, DrawView dv, u32 *state, long long B, long long env0) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    Draw<MODE> d;
+    d.init(dv, e, env0 + e);
+    u32 acc = 0;
+    for (int i = 0; i < nv.n; i++) {  // Graph.genRandState base.py:368-370
+        acc |= (u32)d.randint(0, 2) << (i & 31);
+        if ((i & 31) == 31 || i == nv.n - 1) { state[(long long)(i >> 5) * B + e] = acc; acc = 0; }
+    }
+    d.done(dv, e);
+}
+
+// ----------------------------------------------------------------------------------------------- K3 SSD
+struct SsdParams {
+    int g;
+    int smem_hist;  // 1: per-block shared histogram (g <= 12), 0: global atomics
+    float inv;      // 1/log2(1-p); < 0 = flips disabled
+    double p;
+    short tgt[24];
+};
+
+template <int NET, int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, int has_env, DrawView dv, SsdParams sp, u32 *state,
+                                                   long long chains, long long env0, long long iters,
+                                                   unsigned long long *hist) {
+    unsigned char *blob = smem_raw;
+    unsigned char *img = smem_raw + nv.blob_bytes;
+    const int img_bytes = has_env ? ev.img_bytes : 0;
+    u32 *shist = reinterpret_cast<u32 *>(img + img_bytes);
+    const int nb = 1 << sp.g;
+    u32 *sst = shist + (sp.smem_hist ? nb : 0);
+    stage(blob, nv.blob, nv.blob_bytes);
+    if (has_env) stage(img, ev.img, ev.img_bytes);
+    if (sp.smem_hist)
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) shist[b] = 0;
+    const int *att_off = reinterpret_cast<const int *>(img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w32 = nv.w32, n = nv.n;
+    Col st{sst + threadIdx.x, (int)blockDim.x};
+    if (e < chains) load_state(st, state, chains, e, w32);
+    __syncthreads();
+    if (e < chains) {
+        Draw<MODE> d;
+        d.init(dv, e, env0 + e);
+        u32 pos = 0;
+        if constexpr (MODE == PBN_DRAW_PHILOX) pos = sp.inv < 0.f ? 0xFFFFFFFFu : geom_gap(d.next(), sp.inv);
+        int cur = -1;
+        u32 run = 0;
+        for (long long t = 0; t < iters; t++) {
+            int b = 0;
+            for (int k = 0; k < sp.g; k++) b = (b << 1) | (int)st.bit(sp.tgt[k]);  // MSB-first, pbn_target.py:383-391
+            if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
+                if (run) {
+                    if (sp.smem_hist) atomicAdd(&shist[cur], run);
+                    else atomicAdd(&hist[cur], (unsigned long long)run);
+                }
+                cur = b; run = 0;
+            }
+            run++;
+            if constexpr (MODE == PBN_DRAW_REPLAY) {
+                for (int j = 0; j < n; j++)
+                    if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
+            } else {
+                if (sp.inv >= 0.f) {
+                    while (pos < (u32)n) { st.flip((int)pos); pos += 1u + geom_gap(d.next(), sp.inv); }
+                    pos -= (u32)n;
+                }
+            }
+            micro_step<NET, MODE>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
+            if (has_env && !ev.force) {
+                int in = 1;
+                while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE>(nv, blob, st, d); in++; }
+            }
+        }
+        if (run) {
+            if (sp.smem_hist) atomicAdd(&shist[cur], run);
+            else atomicAdd(&hist[cur], (unsigned long long)run);
+        }
+        store_state(st, state, chains, e, w32);
+        d.done(dv, e);
+    }
+    if (sp.smem_hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+            if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- pack / unpack
+__global__ void k_unpack(const u32 *state, long long B, int n, unsigned char *out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * n) return;
+    const long long e = idx / n;
+    const int i = (int)(idx - e * n);
+    out[idx] = (unsigned char)((state[(long long)(i >> 5) * B + e] >> (i & 31)) & 1u);
+}
+__global__ void k_pack(const unsigned char *in, long long B, int n, int w32, u32 *state) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * w32) return;
+    const long long e = idx % B;
+    const int w = (int)(idx / B);
+    u32 acc = 0;
+    for (int b = 0; b < 32 && w * 32 + b < n; b++) acc |= (u32)(in[e * n + w * 32 + b] != 0) << b;
+    state[(long long)w * B + e] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------- issue-peak microbenchmarks
+__global__ void __launch_bounds__(256) k_peak_alu(long long iters, u32 *sink) {
+    u32 a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3, a4 = a0 ^ 0x55, a5 = a0 + 9, a6 = ~a0, a7 = a0 << 3;
+    const u32 k = blockIdx.x | 1;
+    for (long long t = 0; t < iters; t++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {  // 8 independent chains x 2 ops (LOP3 + IADD3) x 8 = 128 ops / iteration
+            a0 = (a0 ^ k) + a1; a1 = (a1 ^ k) + a2; a2 = (a2 ^ k) + a3; a3 = (a3 ^ k) + a4;
+            a4 = (a4 ^ k) + a5; a5 = (a5 ^ k) + a6; a6 = (a6 ^ k) + a7; a7 = (a7 ^ k) + a0;
+        }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) sink[0] = a0;
+}
+__global__ void __launch_bounds__(256) k_peak_philox(long long iters, u32 *sink) {
+    u32 acc = 0, o0, o1, o2, o3;
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long t = 0; t < iters; t++) {
+        philox4x32_10((u32)t, 0, tid, 0, 1234u, 5678u, o0, o1, o2, o3);
+        acc ^= o0 ^ o1 ^ o2 ^ o3;
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
+extern "C" int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double *ops_out) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    u32 *sink = nullptr;
+    CK(cudaMalloc(&sink, 4));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int grid = sms * 8, block = 256;
+    for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+        CK(cudaEventRecord(a));
+        if (kind == 0) k_peak_alu<<<grid, block>>>(iters, sink);
+        else k_peak_philox<<<grid, block>>>(iters, sink);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventElapsedTime(ms_out, a, b));
+    *ops_out = (double)grid * block * (double)iters * (kind == 0 ? 128.0 : 1.0);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    return PBN_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- launch glue
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PBN_OK;
+}
+static inline int block_for(long long B) { return B >= PBN_BLOCK ? PBN_BLOCK : (int)(((B + 31) / 32) * 32); }
+
+#define DISPATCH(NETKIND, MODE, CALL)                                                       \
+    do {                                                                                    \
+        if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX); } \
+        else if ((NETKIND) == PBN_NET_PRED) { CALL(PBN_NET_PRED, PBN_DRAW_REPLAY); }        \
+        else if ((MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_TT, PBN_DRAW_PHILOX); }          \
+        else { CALL(PBN_NET_TT, PBN_DRAW_REPLAY); }                                         \
+    } while (0)
+
+static int check_draws(const PbnDraws *d) {
+    if (!d) return fail(PBN_ERR_ARG, "draws is null");
+    if (d->mode != PBN_DRAW_PHILOX && d->mode != PBN_DRAW_REPLAY) return fail(PBN_ERR_ARG, "unknown draw mode");
+    if (d->mode == PBN_DRAW_REPLAY && (!d->ints || !d->dbls)) return fail(PBN_ERR_ARG, "replay draws need ints and dbls");
+    return PBN_OK;
+}
+
+extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, int64_t steps, int32_t sync,
+                           const PbnDraws *draws, void *stream) {
+    if (!net || !state || B < 0 || steps < 0) return fail(PBN_ERR_ARG, "bad argument");
+    if (int rc = check_draws(draws)) return rc;
+    if (B == 0 || steps == 0) return PBN_OK;
+    const NetView &nv = net->v;
+    const DrawView dv = make_draws(draws);
+    const int block = block_for(B);
+    const unsigned grid = (unsigned)((B + block - 1) / block);
+    const size_t smem = (size_t)nv.blob_bytes + (size_t)2 * nv.w32 * block * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+#define CALL(NK, MD)                                                               \
+    if (int rc = set_smem(k_rollout<NK, MD>, smem)) return rc;                     \
+    k_rollout<NK, MD><<<grid, block, smem, s>>>(nv, dv, state, B, env0, steps, sync)
+    DISPATCH(nv.kind, dv.mode, CALL);
+#undef CALL
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
+extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                            const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
+                            uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
+                            void *stream) {
+    if (!env || !state || !actions || !reward || !terminated || !truncated || B < 0 || K < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if ((env->v.kind == PBN_ENV_TARGET || env->v.kind == PBN_ENV_MULTI) && (!n_steps || !target_att))
+        return fail(PBN_ERR_ARG, "target envs need n_steps and target_att");
+    if ((env->v.kind == PBN_ENV_PBN_SD && K != 2) || (env->v.kind == PBN_ENV_PBCN_SD && K != 1 + env->v.n_control))
+        return fail(PBN_ERR_ARG, "wrong action width for this env kind");
+    if (int rc = check_draws(draws)) return rc;
+    if (B == 0) return PBN_OK;
+    const NetView &nv = env->net->v;
+    const EnvView &ev = env->v;
+    const DrawView dv = make_draws(draws);
+    const int block = block_for(B);
+    const unsigned grid = (unsigned)((B + block - 1) / block);
+    const size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+#define CALL(NK, MD)                                                                                              \
+    if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                                   \
+    k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state,   \
+                                                 reward, terminated, truncated, inner_steps, B, env0)
+    DISPATCH(nv.kind, dv.mode, CALL);
+#undef CALL
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
+extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                             const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream) {
+    if (!env || !state || B < 0) return fail(PBN_ERR_ARG, "bad argument");
+    const EnvView &ev = env->v;
+    if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
+        if (!n_steps || !target_att) return fail(PBN_ERR_ARG, "target envs need n_steps and target_att");
+        if (ev.n_att < (ev.kind == PBN_ENV_TARGET ? 2 : 1)) return fail(PBN_ERR_ARG, "reset needs attractors (sample of 2, pbn_target.py:333)");
+    } else if (ev.n_att < 1) return fail(PBN_ERR_ARG, "reset needs attractors");
+    if (int rc = check_draws(draws)) return rc;
+    if (B == 0) return PBN_OK;
+    const DrawView dv = make_draws(draws);
+    const int block = block_for(B);
+    const unsigned grid = (unsigned)((B + block - 1) / block);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dv.mode == PBN_DRAW_PHILOX)
+        k_env_reset<PBN_DRAW_PHILOX><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0);
+    else
+        k_env_reset<PBN_DRAW_REPLAY><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
+extern "C" int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, const PbnDraws *draws, void *stream) {
+    if (!net || !state || B < 0) return fail(PBN_ERR_ARG, "bad argument");
+    if (int rc = check_draws(draws)) return rc;
+    if (B == 0) return PBN_OK;
+    const DrawView dv = make_draws(draws);
+    const int block = block_for(B);
+    const unsigned grid = (unsigned)((B + block - 1) / block);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dv.mode == PBN_DRAW_PHILOX) k_rand_state<PBN_DRAW_PHILOX><<<grid, block, 0, s>>>(net->v, dv, state, B, env0);
+    else k_rand_state<PBN_DRAW_REPLAY><<<grid, block, 0, s>>>(net->v, dv, state, B, env0);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
+extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chains, int64_t env0, int64_t iters,
+                       double p, const int32_t *tgt, int32_t g, uint64_t *hist, const PbnDraws *draws, void *stream) {
+    if (!net || !state || !tgt || !hist || chains < 0 || iters < 0) return fail(PBN_ERR_ARG, "bad argument");
+    if (g < 1 || g > 24) return fail(PBN_ERR_ARG, "1 <= g <= 24 target nodes");
+    if (!(p >= 0.0 && p <= 1.0)) return fail(PBN_ERR_ARG, "Invalid Bit Flip Probability value.");  // eval.py:31-33
+    if (env && env->net != net) return fail(PBN_ERR_ARG, "env belongs to another network");
+    if (int rc = check_draws(draws)) return rc;
+    if (chains == 0 || iters == 0) return PBN_OK;
+    const NetView &nv = net->v;
+    const DrawView dv = make_draws(draws);
+    SsdParams sp;
+    sp.g = g; sp.p = p; sp.smem_hist = g <= 12;
+    sp.inv = p <= 0 ? -1.0f : (p >= 1 ? 0.0f : (float)(1.0 / std::log2(1.0 - p)));
+    for (int k = 0; k < g; k++) {
+        if (tgt[k] < 0 || tgt[k] >= nv.n) return fail(PBN_ERR_ARG, "target node out of range");
+        sp.tgt[k] = (short)tgt[k];
+    }
+    const int block = block_for(chains);
+    if (sp.smem_hist && (double)iters * block >= 4294967296.0) return fail(PBN_ERR_ARG, "iters too large for one launch; split the estimate");
+    const unsigned grid = (unsigned)((chains + block - 1) / block);
+    EnvView ev;
+    memset(&ev, 0, sizeof ev);
+    if (env) ev = env->v;
+    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+#define CALL(NK, MD)                                                                                      \
+    if (int rc = set_smem(k_ssd<NK, MD>, smem)) return rc;                                                \
+    k_ssd<NK, MD><<<grid, block, smem, s>>>(nv, ev, env ? 1 : 0, dv, sp, state, chains, env0, iters,      \
+                                            (unsigned long long *)hist)
+    DISPATCH(nv.kind, dv.mode, CALL);
+#undef CALL
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
+extern "C" int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t env0, int64_t iters, double p,
+                            const int32_t *tgt, int32_t g, uint64_t seed, uint32_t epoch, uint64_t *hist_host) {
+    if (!net || !hist_host || chains < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if (g < 1 || g > 24) return fail(PBN_ERR_ARG, "1 <= g <= 24 target nodes");
+    u32 *state = nullptr;
+    uint64_t *hist = nullptr;
+    CK(cudaMalloc(&state, (size_t)net->v.w32 * chains * 4));
+    CK(cudaMalloc(&hist, (size_t)8 << g));
+    CK(cudaMemsetAsync(hist, 0, (size_t)8 << g, 0));
+    PbnDraws d;
+    memset(&d, 0, sizeof d);
+    d.mode = PBN_DRAW_PHILOX; d.seed = seed; d.epoch = epoch;
+    int rc = pbn_rand_state(net, state, chains, env0, &d, nullptr);
+    d.epoch = epoch + 1;
+    if (!rc) rc = pbn_ssd(net, env, state, chains, env0, iters, p, tgt, g, hist, &d, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(hist_host, hist, (size_t)8 << g, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PBN_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(state);
+    cudaFree(hist);
+    return rc;
+}
+
+extern "C" int pbn_unpack_state(const uint32_t *state, int64_t B, int32_t n, uint8_t *out, void *stream) {
+    if (!state || !out || B < 0 || n < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if (B == 0) return PBN_OK;
+    const long long total = (long long)B * n;
+    k_unpack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, B, n, out);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+extern "C" int pbn_pack_state(const uint8_t *in, int64_t B, int32_t n, uint32_t *state, void *stream) {
+    if (!state || !in || B < 0 || n < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if (B == 0) return PBN_OK;
+    const int w32 = (n + 31) / 32;
+    const long long total = (long long)B * w32;
+    k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, B, n, w32, state);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}

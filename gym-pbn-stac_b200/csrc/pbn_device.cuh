@@ -1,0 +1,251 @@
+// pbn_device.cuh — device-side building blocks of the sm_100a PB(C)N kernels.
+//
+//   * Philox4x32-10 counter-based stream, one sequential stream per env (key = seed,
+//     counter = (block, epoch, env_lo, env_hi)); 31-bit integer thresholds for every decision.
+//   * replay stream: recorded draws of the reference's RNGs, float64 compares exactly as
+//     common/node.py:37-38 and bittner/base.py:94-97 do them.
+//   * bit-packed state in shared memory, one column per thread (word w of thread t at
+//     s[w*blockDim + t]): dynamic bit indexing is a conflict-free LDS, never a register select.
+//   * packed network image staged once per block into shared memory.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pbn_b200.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ----------------------------------------------------------------------------------------------- views
+// Packed network image (what pbn_net_create builds).  All offsets are in bytes from `blob`.
+//   PRED: thr  u32 [N][ts]      cumulative 31-bit thresholds, padded with 0x80000000 (never <= r31)
+//         rec  uint2 [N][fmax]  .x = four u8 node indices (in0 | in1<<8 | in2<<16 | self<<24), .y = 16-bit LUT
+//   TT  : node uint2 [N]        .x = table offset, .y = in_off | k<<16
+//         in   u16 []           input node indices (first = MSB of the table index)
+//         thr  u32 []           31-bit thresholds ceil(P * 2^31)
+struct NetView {
+    int kind, n, first, w32;
+    int ts, fmax;
+    int blob_bytes;
+    int off_thr, off_rec, off_node, off_in;
+    const unsigned char *blob;  // device
+    // float64 side tables for replay mode (device, reference form)
+    const int *pr_off;
+    const double *pr_cum, *pr_codsum;
+    const double *tt_prob;
+};
+
+// Packed env image: cubes as (care, value) word pairs.
+struct EnvView {
+    int kind, horizon, max_inner, force, dedup, control_write, n_control;
+    int successful_reward, wrong_attractor_cost;
+    int n_att, n_cubes, tgt_first, n_tgt;
+    int img_bytes;               // bytes of [att_off (n_att+1 ints, padded to 8)] [cubes: n_cubes*w32*2 u32]
+    int off_cubes;
+    const unsigned char *img;    // device
+};
+
+struct DrawView {
+    int mode;
+    u32 epoch;
+    u32 seed_lo, seed_hi;
+    const int *ints;
+    const double *dbls;
+    long long int_stride, dbl_stride;
+    long long *used;
+};
+
+// ----------------------------------------------------------------------------------------------- Philox
+__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 &o0, u32 &o1,
+                                              u32 &o2, u32 &o3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u64 p0 = (u64)0xD2511F53u * c0;
+        u64 p1 = (u64)0xCD9E8D57u * c2;
+        u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
+        u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (u32)p1;
+        c3 = (u32)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+template <int MODE>
+struct Draw;
+
+template <>
+struct Draw<PBN_DRAW_PHILOX> {
+    u32 k0, k1, blk, c1, c2, c3;
+    u32 b0, b1, b2, b3;
+    int have;
+    u32 cnt;
+    __device__ __forceinline__ void init(const DrawView &dv, long long /*local*/, long long env_id) {
+        k0 = dv.seed_lo; k1 = dv.seed_hi;
+        blk = 0; c1 = dv.epoch; c2 = (u32)env_id; c3 = (u32)((u64)env_id >> 32);
+        have = 0; cnt = 0;
+        b0 = b1 = b2 = b3 = 0;
+    }
+    __device__ __forceinline__ u32 next() {
+        if (have == 0) {
+            philox4x32_10(blk, c1, c2, c3, k0, k1, b0, b1, b2, b3);
+            blk++;
+            have = 4;
+        }
+        u32 r = b0;
+        b0 = b1; b1 = b2; b2 = b3;
+        have--;
+        cnt++;
+        return r;
+    }
+    // uniform integer in [lo, lo+n): random.randint(lo, lo+n-1)
+    __device__ __forceinline__ int randint(int lo, int n) { return lo + (int)__umulhi(next(), (u32)n); }
+    __device__ __forceinline__ void done(const DrawView &dv, long long local) {
+        if (dv.used) { dv.used[2 * local] = cnt; dv.used[2 * local + 1] = 0; }
+    }
+};
+
+template <>
+struct Draw<PBN_DRAW_REPLAY> {
+    const int *ip;
+    const double *dp;
+    long long ni, nd;
+    __device__ __forceinline__ void init(const DrawView &dv, long long local, long long /*env_id*/) {
+        ip = dv.ints + local * dv.int_stride;
+        dp = dv.dbls + local * dv.dbl_stride;
+        ni = nd = 0;
+    }
+    __device__ __forceinline__ int randint(int /*lo*/, int /*n*/) { ni++; return *ip++; }  // recorded result
+    __device__ __forceinline__ double dbl() { nd++; return *dp++; }
+    __device__ __forceinline__ void done(const DrawView &dv, long long local) {
+        if (dv.used) { dv.used[2 * local] = ni; dv.used[2 * local + 1] = nd; }
+    }
+};
+
+// ----------------------------------------------------------------------------------------------- geometric gap
+// Number of failures before the next success of a Bernoulli(p) process, from one 32-bit draw:
+//   u = ((r>>9)+0.5)/2^23,  G = trunc(log2(u) * inv),  inv = 1/log2(1-p).
+// log2 is a fixed degree-7 polynomial evaluated with IEEE single fma only (no MUFU), so the CPU oracle
+// (oracle/pbn_oracle.c: orc_geom) reproduces it bit for bit.
+__device__ __forceinline__ float log2f_poly(float x) {
+    u32 b = __float_as_uint(x);
+    int e = (int)(b >> 23) - 127;
+    float m = __uint_as_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421356f) { m = __fmul_rn(m, 0.5f); e += 1; }
+    float t = __fsub_rn(m, 1.0f);
+    float p = -1.427597404e-01f;
+    p = __fmaf_rn(p, t, 2.326525748e-01f);
+    p = __fmaf_rn(p, t, -2.492718250e-01f);
+    p = __fmaf_rn(p, t, 2.872888744e-01f);
+    p = __fmaf_rn(p, t, -3.602251709e-01f);
+    p = __fmaf_rn(p, t, 4.809167087e-01f);
+    p = __fmaf_rn(p, t, -7.213529348e-01f);
+    p = __fmaf_rn(p, t, 1.442695022e+00f);
+    return __fmaf_rn(p, t, (float)e);
+}
+__device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
+    float u = __fmul_rn(__fadd_rn((float)(r >> 9), 0.5f), 1.0f / 8388608.0f);
+    float g = __fmul_rn(log2f_poly(u), inv);
+    if (!(g < 1.0e9f)) return 1000000000u;
+    return (u32)g;  // g >= 0: truncation
+}
+
+// ----------------------------------------------------------------------------------------------- state column
+struct Col {
+    u32 *s;      // &state_smem[threadIdx.x]
+    int stride;  // blockDim.x
+    __device__ __forceinline__ u32 word(int w) const { return s[w * stride]; }
+    __device__ __forceinline__ void set_word(int w, u32 v) const { s[w * stride] = v; }
+    __device__ __forceinline__ u32 bit(int pos) const { return (s[(pos >> 5) * stride] >> (pos & 31)) & 1u; }
+    __device__ __forceinline__ void flip(int pos) const { s[(pos >> 5) * stride] ^= 1u << (pos & 31); }
+    __device__ __forceinline__ void put(int pos, u32 v) const {
+        u32 *p = s + (pos >> 5) * stride;
+        u32 m = 1u << (pos & 31);
+        *p = (*p & ~m) | (v ? m : 0u);
+    }
+};
+
+// ----------------------------------------------------------------------------------------------- node updates
+// bittner/base.py:89-119 Node.Predstep.  `blob` is the shared-memory copy of the network image.
+template <int MODE>
+__device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
+    int j;
+    if constexpr (MODE == PBN_DRAW_PHILOX) {
+        u32 r = d.next() >> 1;
+        const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * (nv.ts >> 2);
+        j = 0;
+        for (int q = 0; q < (nv.ts >> 2); q++) {
+            uint4 t = thr[q];
+            j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        }
+    } else {
+        double r = d.dbl() * nv.pr_codsum[i];  // base.py:94
+        int q0 = nv.pr_off[i], q1 = nv.pr_off[i + 1];
+        j = q1 - q0 - 1;  // falls through to the last predictor, base.py:95-97
+        for (int k = q0; k < q1; k++)
+            if (nv.pr_cum[k] > r) { j = k - q0; break; }
+    }
+    uint2 rec = reinterpret_cast<const uint2 *>(blob + nv.off_rec)[i * nv.fmax + j];
+    u32 idx = (st.bit(rec.x & 0xFF) << 3) | (st.bit((rec.x >> 8) & 0xFF) << 2) | (st.bit((rec.x >> 16) & 0xFF) << 1) |
+              st.bit(rec.x >> 24);
+    return (rec.y >> idx) & 1u;
+}
+
+// common/node.py:31-38 Node.compute_next_value
+template <int MODE>
+__device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
+    uint2 nr = reinterpret_cast<const uint2 *>(blob + nv.off_node)[i];
+    const unsigned short *in = reinterpret_cast<const unsigned short *>(blob + nv.off_in) + (nr.y & 0xFFFF);
+    int k = (int)(nr.y >> 16);
+    u32 idx = 0;
+    for (int q = 0; q < k; q++) idx = (idx << 1) | st.bit(in[q]);
+    if constexpr (MODE == PBN_DRAW_PHILOX) {
+        u32 thr = reinterpret_cast<const u32 *>(blob + nv.off_thr)[nr.x + idx];
+        return ((d.next() >> 1) < thr) ? 1u : 0u;
+    } else {
+        return (d.dbl() < nv.tt_prob[nr.x + idx]) ? 1u : 0u;  // u < p, node.py:37-38
+    }
+}
+
+template <int NET, int MODE>
+__device__ __forceinline__ u32 node_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
+    if constexpr (NET == PBN_NET_PRED) return pred_next<MODE>(nv, blob, st, i, d);
+    else return tt_next<MODE>(nv, blob, st, i, d);
+}
+
+// one asynchronous update: PBN.step common/pbn.py:88-92 / PBCN.step common/pbcn.py:59-61 / Graph.step base.py:306-312
+template <int NET, int MODE>
+__device__ __forceinline__ void micro_step(const NetView &nv, const unsigned char *blob, const Col &st, Draw<MODE> &d) {
+    int i = d.randint(nv.first, nv.n - nv.first);
+    u32 v = node_next<NET, MODE>(nv, blob, st, i, d);
+    st.put(i, v);
+}
+
+// Graph.synch_step (perturbations off) base.py:300-303: every node from the OLD state, in node order
+template <int NET, int MODE>
+__device__ __forceinline__ void sync_step(const NetView &nv, const unsigned char *blob, const Col &st, const Col &tmp,
+                                          Draw<MODE> &d) {
+    u32 acc = 0;
+    for (int i = 0; i < nv.n; i++) {
+        acc |= node_next<NET, MODE>(nv, blob, st, i, d) << (i & 31);
+        if ((i & 31) == 31 || i == nv.n - 1) { tmp.set_word(i >> 5, acc); acc = 0; }
+    }
+    for (int w = 0; w < nv.w32; w++) st.set_word(w, tmp.word(w));
+}
+
+// ----------------------------------------------------------------------------------------------- cubes
+// cubes: u32 [n_cubes][w32][2] = (care, value); a state matches iff (word & care) == value for every word.
+__device__ __forceinline__ bool cube_match(const u32 *cubes, int c, const Col &st, int w32) {
+    const u32 *p = cubes + (size_t)c * w32 * 2;
+    bool ok = true;
+    for (int w = 0; w < w32; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
+    return ok;
+}
+__device__ __forceinline__ bool match_range(const u32 *cubes, int c0, int c1, const Col &st, int w32) {
+    for (int c = c0; c < c1; c++)
+        if (cube_match(cubes, c, st, w32)) return true;
+    return false;
+}

@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI declared in include/pbn_b200.h.
+
+The CUDA library is the only compute path: if libpbn_b200.so is missing or fails to load this module
+raises — there is no CPU fallback anywhere in the product.
+"""
+import ctypes as C
+from pathlib import Path
+
+PKG_ROOT = Path(__file__).resolve().parents[2]  # gym-pbn-stac_b200/
+LIB_PATH = PKG_ROOT / "lib" / "libpbn_b200.so"
+
+NET_TT, NET_PRED = 0, 1
+ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD = range(6)
+DRAW_PHILOX, DRAW_REPLAY = 0, 1
+
+
+class PbnNetDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_nodes", C.c_int32), ("first_updatable", C.c_int32),
+                ("tt_in_off", C.c_void_p), ("tt_in", C.c_void_p), ("tt_tab_off", C.c_void_p), ("tt_prob", C.c_void_p),
+                ("pr_off", C.c_void_p), ("pr_in", C.c_void_p), ("pr_lut", C.c_void_p),
+                ("pr_cum", C.c_void_p), ("pr_codsum", C.c_void_p)]
+
+
+class PbnEnvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("horizon", C.c_int32), ("max_inner", C.c_int32), ("force", C.c_int32),
+                ("dedup", C.c_int32), ("control_write", C.c_int32), ("n_control", C.c_int32),
+                ("successful_reward", C.c_int32), ("wrong_attractor_cost", C.c_int32),
+                ("n_att", C.c_int32), ("att_off", C.c_void_p), ("cube", C.c_void_p),
+                ("tgt_first", C.c_int32), ("n_tgt", C.c_int32)]
+
+
+class PbnDraws(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("epoch", C.c_uint32), ("seed", C.c_uint64),
+                ("ints", C.c_void_p), ("dbls", C.c_void_p), ("int_stride", C.c_int64), ("dbl_stride", C.c_int64),
+                ("used", C.c_void_p)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "pbn_net_create": (C.c_int, [C.POINTER(PbnNetDesc), C.POINTER(C.c_void_p)]),
+    "pbn_net_destroy": (C.c_int, [C.c_void_p]),
+    "pbn_net_words": (C.c_int, [C.c_void_p]),
+    "pbn_env_create": (C.c_int, [C.c_void_p, C.POINTER(PbnEnvDesc), C.POINTER(C.c_void_p)]),
+    "pbn_env_destroy": (C.c_int, [C.c_void_p]),
+    "pbn_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                              C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                               C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_rand_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_ssd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                          C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_ssd_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p,
+                               C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "pbn_unpack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pbn_pack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pbn_issue_peak": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+    "pbn_last_error": (C.c_char_p, []),
+    "pbn_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+class PbnError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpbn_b200.so (built in-tree by gym-pbn-stac_b200/build.py).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise PbnError(
+                f"CUDA library not found at {LIB_PATH}. Build it with `python gym-pbn-stac_b200/build.py` "
+                "(nvcc, sm_100a). gym_PBN on B200 has no CPU fallback."
+            )
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().pbn_last_error().decode()
+        if rc == 1:
+            raise ValueError(msg)
+        raise PbnError(f"pbn_b200 error {rc}: {msg}")

@@ -1,0 +1,214 @@
+"""Device-side engine: owns the compiled network / env handles and the per-env state tensors, and
+launches the kernels of libpbn_b200.so on the caller's current CUDA stream.  torch is used for device
+memory and streams only.
+
+State layout (HBM): int32 planes [W32][B]; node i of env e is bit (i & 31) of state[i >> 5, e].
+Every launch gets a fresh Philox epoch; env e of a job uses stream (seed; epoch, env0 + e), so the
+result of a job does not depend on how its envs are split over launches, ranks or GPUs.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+from .compiler import NetworkSpec, compile_cubes
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(device):
+    device = torch.device(device if device is not None else "cuda")
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise abi.PbnError("gym_PBN (B200 build) needs a CUDA device; there is no CPU fallback")
+    return device
+
+
+class Network:
+    """Compiled network handle (immutable; shareable across streams)."""
+
+    def __init__(self, spec: NetworkSpec, device=None):
+        self.spec = spec
+        self.device = require_cuda(device)
+        self.n, self.w32, self.kind = spec.n, spec.w32, spec.kind
+        a = spec.arrays
+        d = abi.PbnNetDesc(kind=spec.kind, n_nodes=spec.n, first_updatable=spec.first_updatable)
+        for k, v in a.items():
+            setattr(d, k, _np_ptr(v))
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_net_create(C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                abi.lib().pbn_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class EnvImage:
+    """Compiled env description (cubes, rewards, horizon) bound to a Network."""
+
+    def __init__(self, net: Network, kind, attractors=(), targets=(), horizon=100, max_inner=1 << 20, force=False,
+                 dedup=True, control_write=False, n_control=0, successful_reward=10, wrong_attractor_cost=2):
+        self.net, self.kind = net, kind
+        self.n_att = len(attractors)
+        cube, off, tgt_first, n_tgt = compile_cubes(net.n, attractors, targets)
+        self._keep = (cube, off)
+        d = abi.PbnEnvDesc(kind=kind, horizon=int(horizon), max_inner=int(max_inner), force=int(bool(force)),
+                           dedup=int(bool(dedup)), control_write=int(bool(control_write)), n_control=int(n_control),
+                           successful_reward=int(successful_reward), wrong_attractor_cost=int(wrong_attractor_cost),
+                           n_att=self.n_att, att_off=_np_ptr(off), cube=_np_ptr(cube), tgt_first=tgt_first, n_tgt=n_tgt)
+        h = C.c_void_p()
+        with torch.cuda.device(net.device):
+            abi.check(abi.lib().pbn_env_create(net.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                abi.lib().pbn_env_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Replay:
+    """Recorded draws for B envs: ints int32 [B][Li], dbls float64 [B][Ld]."""
+
+    def __init__(self, ints, dbls, device, B=None):
+        ints = np.zeros((B or 1, 1), np.int32) if ints is None else np.asarray(ints, np.int32)
+        dbls = np.zeros((B or 1, 1), np.float64) if dbls is None else np.asarray(dbls, np.float64)
+        if ints.ndim == 1:
+            ints = ints.reshape(1, -1)
+        if dbls.ndim == 1:
+            dbls = dbls.reshape(1, -1)
+        if ints.shape[1] == 0:
+            ints = np.zeros((ints.shape[0], 1), np.int32)
+        if dbls.shape[1] == 0:
+            dbls = np.zeros((dbls.shape[0], 1), np.float64)
+        self.ints = torch.from_numpy(np.ascontiguousarray(ints)).to(device)
+        self.dbls = torch.from_numpy(np.ascontiguousarray(dbls)).to(device)
+        self.used = torch.zeros((self.ints.shape[0], 2), dtype=torch.int64, device=device)
+
+    def struct(self):
+        return abi.PbnDraws(mode=abi.DRAW_REPLAY, ints=_ptr(self.ints), dbls=_ptr(self.dbls),
+                            int_stride=self.ints.shape[1], dbl_stride=self.dbls.shape[1], used=_ptr(self.used))
+
+
+class Simulator:
+    """B envs of one network on one GPU."""
+
+    def __init__(self, net: Network, num_envs: int, seed: int = 0, env0: int = 0):
+        self.net, self.B, self.env0 = net, int(num_envs), int(env0)
+        self.device = net.device
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.epoch = 0
+        self.state = torch.zeros((net.w32, self.B), dtype=torch.int32, device=self.device)
+        self.n_steps = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.target_att = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.target_state = torch.zeros((net.w32, self.B), dtype=torch.int32, device=self.device)
+        self.obs_state = torch.zeros((net.w32, self.B), dtype=torch.int32, device=self.device)
+        self.reward = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.terminated = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        self.truncated = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        self.inner = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.launches = 0
+
+    # ---- draws
+    def reseed(self, seed):
+        self.seed, self.epoch = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+    def _draws(self, replay=None):
+        if replay is not None:
+            return replay.struct()
+        d = abi.PbnDraws(mode=abi.DRAW_PHILOX, seed=self.seed, epoch=self.epoch & 0xFFFFFFFF)
+        self.epoch += 1
+        return d
+
+    # ---- state in / out
+    def set_state(self, bits):
+        """bits: uint8/bool [B][N] (host array or tensor)."""
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(bits, dtype=np.uint8)) if not torch.is_tensor(bits) else bits)
+        t = t.to(self.device, dtype=torch.uint8).reshape(self.B, self.net.n).contiguous()
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_pack_state(_ptr(t), self.B, self.net.n, _ptr(self.state), _stream()))
+            self.launches += 1
+
+    def unpack(self, planes=None):
+        """uint8 [B][N] device tensor of the packed planes (default: the live state)."""
+        planes = self.state if planes is None else planes
+        out = torch.empty((self.B, self.net.n), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_unpack_state(_ptr(planes), self.B, self.net.n, _ptr(out), _stream()))
+            self.launches += 1
+        return out
+
+    # ---- kernels
+    def rand_state(self, replay=None):
+        d = self._draws(replay)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_rand_state(self.net.handle, _ptr(self.state), self.B, self.env0, C.byref(d), _stream()))
+            self.launches += 1
+
+    def rollout(self, steps, sync=False, replay=None):
+        d = self._draws(replay)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_rollout(self.net.handle, _ptr(self.state), self.B, self.env0, int(steps), int(bool(sync)),
+                                            C.byref(d), _stream()))
+            self.launches += 1
+
+    def env_step(self, env: EnvImage, actions, replay=None):
+        """actions: int32 device tensor [B] or [B][K].  Results land in self.reward / terminated / truncated / inner /
+        obs_state (overwritten by the next call)."""
+        actions = actions.to(self.device, dtype=torch.int32).reshape(self.B, -1).contiguous()
+        d = self._draws(replay)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_env_step(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                             _ptr(actions), actions.shape[1], _ptr(self.obs_state), _ptr(self.reward),
+                                             _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner), self.B,
+                                             self.env0, C.byref(d), _stream()))
+            self.launches += 1
+
+    def env_reset(self, env: EnvImage, mask=None, replay=None):
+        if mask is not None:
+            mask = mask.to(self.device, dtype=torch.uint8).contiguous()
+        d = self._draws(replay)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_env_reset(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                              _ptr(self.target_state), _ptr(mask), self.B, self.env0, C.byref(d), _stream()))
+            self.launches += 1
+
+    def ssd(self, iters, bit_flip_prob, tgt_nodes, env: EnvImage = None, hist=None, replay=None):
+        """Accumulates the visit histogram of B chains x iters iterations into hist (int64 [2^g], device)."""
+        tgt = np.ascontiguousarray(tgt_nodes, np.int32)
+        g = len(tgt)
+        if hist is None:
+            hist = torch.zeros(1 << g, dtype=torch.int64, device=self.device)
+        d = self._draws(replay)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_ssd(self.net.handle, env.handle if env is not None else None, _ptr(self.state), self.B,
+                                        self.env0, int(iters), float(bit_flip_prob), _np_ptr(tgt), g, _ptr(hist),
+                                        C.byref(d), _stream()))
+            self.launches += 1
+        return hist
+
+
+def issue_peak(kind, iters=2000):
+    """(ops/s) of the instruction-issue microbenchmarks: kind 0 = INT ALU ops, kind 1 = Philox4x32-10 blocks."""
+    ms, ops = C.c_float(), C.c_double()
+    abi.check(abi.lib().pbn_issue_peak(kind, iters, C.byref(ms), C.byref(ops)))
+    return ops.value / (ms.value * 1e-3), ms.value

@@ -1,0 +1,158 @@
+/*
+ * pbn_b200.h — C-ABI of the B200-native PB(C)N simulator (libpbn_b200.so).
+ *
+ * The reference (jakub-zarzycki2022/gym-PBN-stac) is pure Python and has no FFI; this ABI sits
+ * *below* the drop-in gymnasium classes (gym_PBN.envs.*) and is what they call through ctypes.
+ * Every entry point cites the reference interface it replaces.  Plain pointers and sizes only:
+ * no torch types.  Unless a name ends in `_host`, every data pointer is a DEVICE pointer and the
+ * call only enqueues work on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *
+ * All functions return 0 on success or a PBN_ERR_* code; nothing throws across the boundary.
+ * pbn_last_error() returns a thread-local message for the last failure.
+ *
+ * Layouts
+ *   state      uint32 planes [W32][B], W32 = ceil(N/32); node i of env e = bit (i&31) of state[(i>>5)*B + e]
+ *   actions    int32 [B][K] row-major
+ *   histogram  uint64 [2^g], bucket = target-node bits MSB-first (pbn_target.py:383-391)
+ */
+#ifndef PBN_B200_H
+#define PBN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBN_OK 0
+#define PBN_ERR_ARG 1         /* bad argument / unsupported size */
+#define PBN_ERR_CUDA 2        /* CUDA runtime error (message in pbn_last_error) */
+#define PBN_ERR_UNSUPPORTED 3
+
+/* network kinds */
+#define PBN_NET_TT 0   /* truth-table PBN / PBCN: gym_PBN/envs/common/{node,pbn,pbcn}.py */
+#define PBN_NET_PRED 1 /* Bittner predictor graph: gym_PBN/envs/bittner/base.py Node/Graph */
+
+/* Host-side description handed to the network compiler (arrays are HOST pointers, copied once). */
+typedef struct {
+    int32_t kind;
+    int32_t n_nodes;
+    int32_t first_updatable; /* randint lower bound: 1 = PBN.step (common/pbn.py:90), 0 = Graph.step (base.py:308) */
+    /* PBN_NET_TT: node i reads tt_in[tt_in_off[i]..tt_in_off[i+1]) (ascending node index, first = MSB of the
+       table index, common/node.py:31-32); P(next=1) = tt_prob[tt_tab_off[i] + idx] */
+    const int32_t *tt_in_off;  /* [N+1] */
+    const int32_t *tt_in;
+    const int32_t *tt_tab_off; /* [N+1] */
+    const double *tt_prob;
+    /* PBN_NET_PRED: node i owns predictors pr_off[i]..pr_off[i+1); predictor q reads nodes pr_in[4q..4q+3]
+       (3 inputs, then the node itself: base.py:100-104); pr_lut[q] bit (x0<<3|x1<<2|x2<<1|x3) = [X.A >= 0]
+       tabulated on the host with the reference's float expression (base.py:110-118); pr_cum = cumulative COD
+       (base.py:30-45); pr_codsum[i] = CODsum */
+    const int32_t *pr_off; /* [N+1] */
+    const int32_t *pr_in;
+    const uint16_t *pr_lut;
+    const double *pr_cum;
+    const double *pr_codsum; /* [N] */
+} PbnNetDesc;
+
+typedef struct PbnNet PbnNet; /* opaque; immutable after creation, shareable across streams */
+
+/* Network compiler back end: lowers the description into the packed device image (gather indices, 16-bit LUTs,
+   31-bit integer thresholds) that kernels stage into shared memory.  Replaces PBN.__init__ / Node.__init__
+   (common/pbn.py:16-46, common/node.py:6-26) and Node.add_predictors (base.py:30-45). */
+int pbn_net_create(const PbnNetDesc *desc, PbnNet **out);
+int pbn_net_destroy(PbnNet *net);
+int pbn_net_words(const PbnNet *net); /* W32 */
+
+/* Environment kinds: one per reference env class on the hot path. */
+#define PBN_ENV_PBN 0     /* PBNEnv             pbn_env.py:125-188 */
+#define PBN_ENV_PBCN 1    /* PBCNEnv            pbcn_env.py:52-80 */
+#define PBN_ENV_TARGET 2  /* PBNTargetEnv       pbn_target.py:241-326 (+ Bittner7.is_attracting_state :562-574) */
+#define PBN_ENV_MULTI 3   /* PBNTargetMultiEnv  pbn_target_multi.py:119-225 */
+#define PBN_ENV_PBN_SD 4  /* PBNSampledDataEnv  sampled_data.py:52-88 */
+#define PBN_ENV_PBCN_SD 5 /* PBCNSampledDataEnv sampled_data.py:139-189 */
+
+typedef struct {
+    int32_t kind;
+    int32_t horizon;   /* truncated = (n_steps == horizon), pbn_target.py:325 */
+    int32_t max_inner; /* cap on updates per env.step (the reference loop is unbounded, pbn_target.py:270-271) */
+    int32_t force;     /* PBNTargetEnv.step(force=True): exactly one update */
+    int32_t dedup;     /* multi: 1 = tensor actions (unique()'d), 0 = python list, pbn_target_multi.py:120-121 */
+    int32_t control_write; /* PBCN sampled-data: 0 = reference (control never reaches the dynamics), 1 = state[0:M] <- control */
+    int32_t n_control;
+    int32_t successful_reward, wrong_attractor_cost; /* PBCNEnv._get_reward pbcn_env.py:52-65 */
+    /* attractor a owns cubes att_off[a]..att_off[a+1); cube c = cube[c*N..(c+1)*N), values 0/1/2 ('*').
+       n_att == 0 means every state is attracting.  HOST pointers, copied once. */
+    int32_t n_att;
+    const int32_t *att_off;
+    const int8_t *cube;
+    int32_t tgt_first, n_tgt; /* PBN family: the target set = cubes tgt_first .. tgt_first+n_tgt (full states) */
+} PbnEnvDesc;
+
+typedef struct PbnEnv PbnEnv;
+int pbn_env_create(const PbnNet *net, const PbnEnvDesc *desc, PbnEnv **out);
+int pbn_env_destroy(PbnEnv *env);
+
+/* Draw source.  PHILOX: Philox4x32-10, key = seed, counter = (block, epoch, env_lo, env_hi); env e consumes
+   its own stream sequentially, so results do not depend on how envs are split over launches or GPUs.
+   REPLAY: recorded draws of the reference's RNGs, row e = ints + e*int_stride etc. */
+#define PBN_DRAW_PHILOX 0
+#define PBN_DRAW_REPLAY 1
+typedef struct {
+    int32_t mode;
+    uint32_t epoch;
+    uint64_t seed;
+    const int32_t *ints; /* device */
+    const double *dbls;  /* device */
+    int64_t int_stride, dbl_stride;
+    int64_t *used; /* device, optional [B][2]: draws consumed per env */
+} PbnDraws;
+
+/* K1 — `steps` updates of B envs in one launch, state resident on chip.
+   sync=0: PBN.step (common/pbn.py:88-92) / Graph.step (base.py:306-312); sync=1: Graph.synch_step (base.py:300-303). */
+int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, int64_t steps, int32_t sync,
+                const PbnDraws *draws, void *stream);
+
+/* K2 — one env.step for B envs: intervention -> update(s) until attracting (cap) -> reward/terminated/truncated.
+   actions [B][K]: PBN/PBCN/TARGET K=1; MULTI K slots (<0 = absent); PBN_SD (action, interval);
+   PBCN_SD (interval, control bits...).  obs_state (optional) receives the packed observation planes (differs from
+   `state` only for MULTI's pre-update capture, pbn_target_multi.py:133-135). */
+int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                 const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
+                 uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* reset of the envs selected by mask (NULL = all): PBNTargetEnv.reset pbn_target.py:328-352,
+   PBNTargetMultiEnv.reset pbn_target_multi.py:227-259, PBNEnv.reset pbn_env.py:190-213 (+ PBN.reset common/pbn.py:55-78). */
+int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                  const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* Graph.genRandState base.py:368-370 */
+int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* K3 — utils/eval.py:76-103 _ssd_run for `chains` chains x `iters` iterations (model=None), histogram summed over
+   chains into hist[2^g] (uint64, accumulated: caller zeroes).  env may be NULL (= one update per iteration). */
+int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chains, int64_t env0, int64_t iters,
+            double bit_flip_prob, const int32_t *tgt_nodes_host, int32_t g, uint64_t *hist, const PbnDraws *draws,
+            void *stream);
+
+/* Same estimate with HOST buffers: uploads nothing but the description, draws random start states on device
+   (genRandState), runs K3 and copies the histogram back; blocks until done.  The call compute_ssd_hist maps to. */
+int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t env0, int64_t iters,
+                 double bit_flip_prob, const int32_t *tgt_nodes_host, int32_t g, uint64_t seed, uint32_t epoch,
+                 uint64_t *hist_host);
+
+/* layout helpers: packed planes <-> uint8 [B][N] (what env.render()/get_state() hand out, pbn_target.py:354-355) */
+int pbn_unpack_state(const uint32_t *state, int64_t B, int32_t n_nodes, uint8_t *out, void *stream);
+int pbn_pack_state(const uint8_t *in, int64_t B, int32_t n_nodes, uint32_t *state, void *stream);
+
+/* instruction-issue microbenchmarks used by bench.py for the roofline denominator:
+   kind 0 = dependent-free LOP3/IADD3 chain, kind 1 = Philox4x32-10 blocks.  Writes elapsed ms and the number of
+   thread-level operations executed. */
+int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double *ops_out);
+
+const char *pbn_last_error(void);
+const char *pbn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,380 @@
+"""GPU: the CUDA path (through the C-ABI) against (a) golden traces recorded from the reference, replayed
+draw for draw, and (b) the C oracle in Philox mode at larger sizes.  Everything here is bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle as orc  # noqa: E402
+from golden_util import Traj, cubes_to_attractors, load, pbn_data_from  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gym_PBN.b200 import abi, compiler, engine
+
+    class E:
+        pass
+
+    e = E()
+    e.abi, e.compiler, e.engine = abi, compiler, engine
+    return e
+
+
+def _state_np(sim):
+    return sim.unpack().cpu().numpy()
+
+
+def _replay(eng, ints, dbls):
+    return eng.engine.Replay(np.asarray(ints, np.int32).reshape(1, -1), np.asarray(dbls, np.float64).reshape(1, -1), "cuda", B=1)
+
+
+def _used(rp):
+    return tuple(rp.used.cpu().numpy()[0])
+
+
+# ------------------------------------------------------------------------------------------------ golden replays
+@pytest.mark.parametrize("name", ["b28_graph_core.npz", "b100_graph_core.npz", "b200_graph_core.npz"])
+def test_golden_graph_core(eng, name):
+    z = load(name)
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    for e in range(int(z["n_traj"])):
+        tr = Traj(z, e)
+        sim = eng.engine.Simulator(net, 1)
+        rp = _replay(eng, *tr.draws(0))
+        sim.rand_state(replay=rp)
+        assert np.array_equal(_state_np(sim)[0], tr.state[0])
+        # async segment in ONE launch per flip-free stretch would hide per-step states; go op by op
+        for t in range(1, tr.T):
+            ints, dbls = tr.draws(t)
+            rp = _replay(eng, ints, dbls)
+            if tr.op[t] == 0:
+                a = int(tr.act[t, 0])
+                if a >= 0:
+                    sim.state[a >> 5, 0] ^= np.int32(np.uint32(1 << (a & 31)).view(np.int32))
+                sim.rollout(1, replay=rp)
+            else:
+                sim.rollout(1, sync=True, replay=rp)
+            assert _used(rp) == (len(ints), len(dbls))
+            assert np.array_equal(_state_np(sim)[0], tr.state[t]), (name, e, t)
+
+
+def test_golden_graph_core_multistep(eng):
+    """400 async updates of the golden trace in a single launch (state stays on chip)."""
+    z = load("b100_graph_core.npz")
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    tr = Traj(z, 0)
+    # stretches between flips: 5 steps each
+    sim = eng.engine.Simulator(net, 1)
+    sim.set_state(tr.state[0:1])
+    t = 1
+    while t < tr.T and tr.op[t] == 0:
+        a = int(tr.act[t, 0])
+        if a >= 0:
+            sim.state[a >> 5, 0] ^= np.int32(np.uint32(1 << (a & 31)).view(np.int32))
+        t1 = t + 1
+        while t1 < tr.T and tr.op[t1] == 0 and tr.act[t1, 0] < 0:
+            t1 += 1
+        ints, dbls = tr.draws(t, t1)
+        sim.rollout(t1 - t, replay=_replay(eng, ints, dbls))
+        assert np.array_equal(_state_np(sim)[0], tr.state[t1 - 1]), t
+        t = t1
+
+
+def test_golden_tt_core(eng):
+    z = load("tt40_core.npz")
+    net = eng.engine.Network(eng.compiler.compile_pbn_data([(m, t, f"n{i}", False) for i, (m, t) in enumerate(pbn_data_from(z))]))
+    tr = Traj(z, 0)
+    sim = eng.engine.Simulator(net, 1)
+    sim.set_state(tr.state[0:1])
+    for t in range(1, tr.T):
+        ints, dbls = tr.draws(t)
+        rp = _replay(eng, ints, dbls)
+        a = int(tr.act[t, 0])
+        if a >= 0:
+            sim.state[a >> 5, 0] ^= np.int32(np.uint32(1 << (a & 31)).view(np.int32))
+        sim.rollout(1, replay=rp)
+        assert _used(rp) == (len(ints), len(dbls))
+        assert np.array_equal(_state_np(sim)[0], tr.state[t]), t
+
+
+def _run_env_trace(eng, net, env, tr, K):
+    sim = eng.engine.Simulator(net, 1)
+    for t in range(tr.T):
+        ints, dbls = tr.draws(t)
+        rp = _replay(eng, ints, dbls)
+        if tr.op[t] == 1:
+            sim.env_reset(env, replay=rp)
+            assert _used(rp) == (len(ints), len(dbls))
+            assert np.array_equal(_state_np(sim)[0], tr.state[t]), ("reset", t)
+            if tr.target_att[t] >= 0:
+                assert int(sim.target_att[0]) == tr.target_att[t]
+        else:
+            sim.env_step(env, torch.from_numpy(tr.act[t:t + 1, :K].copy()), replay=rp)
+            assert _used(rp) == (len(ints), len(dbls)), t
+            assert np.array_equal(_state_np(sim)[0], tr.state[t]), ("state", t)
+            assert np.array_equal(sim.unpack(sim.obs_state).cpu().numpy()[0], tr.obs[t]), ("obs", t)
+            got = (int(sim.reward[0]), int(sim.terminated[0]), int(sim.truncated[0]))
+            assert got == (tr.reward[t], tr.term[t], tr.trunc[t]), ("reward", t)
+
+
+def test_golden_pbn_env_ex5(eng):
+    z = load("ex5_pbnenv.npz")
+    net = eng.engine.Network(eng.compiler.compile_pbn_data([(m, t, f"n{i}", False) for i, (m, t) in enumerate(pbn_data_from(z))]))
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = eng.engine.EnvImage(net, eng.abi.ENV_PBN, attractors=atts, targets=[tuple(t) for t in z["targets"]])
+    for e in range(int(z["n_traj"])):
+        _run_env_trace(eng, net, env, Traj(z, e), 1)
+
+
+def test_golden_pbcn_and_sampled_data(eng):
+    z = load("ex5_pbcn_sampled.npz")
+    net = eng.engine.Network(eng.compiler.compile_pbn_data([(m, t, f"n{i}", False) for i, (m, t) in enumerate(pbn_data_from(z))]))
+    kinds = [eng.abi.ENV_PBCN, eng.abi.ENV_PBCN_SD, eng.abi.ENV_PBN_SD]
+    for e, kind in enumerate(kinds):
+        atts = cubes_to_attractors(z[f"e{e}/att_cubes"], z[f"e{e}/att_off"])
+        env = eng.engine.EnvImage(net, kind, attractors=atts, targets=[tuple(t) for t in z["targets"]],
+                                  n_control=int(z[f"e{e}/M"]), successful_reward=int(z[f"e{e}/successful_reward"]),
+                                  wrong_attractor_cost=int(z[f"e{e}/wrong_attractor_cost"]))
+        _run_env_trace(eng, net, env, Traj(z, e), 1 if e == 0 else 2)
+
+
+def test_golden_target_env(eng):
+    z = load("b28_target_env.npz")
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    for e in range(int(z["n_traj"])):
+        env = eng.engine.EnvImage(net, eng.abi.ENV_TARGET, attractors=atts, horizon=int(z["horizon"]),
+                                  max_inner=int(z["cap"]), force=bool(z[f"e{e}/force"]))
+        _run_env_trace(eng, net, env, Traj(z, e), 1)
+
+
+def test_golden_multi_env(eng):
+    z = load("b28_multi_env.npz")
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    for e in range(int(z["n_traj"])):
+        env = eng.engine.EnvImage(net, eng.abi.ENV_MULTI, attractors=atts, horizon=int(z["horizon"]),
+                                  max_inner=int(z["cap"]), dedup=bool(z[f"e{e}/dedup"]))
+        _run_env_trace(eng, net, env, Traj(z, e), 3)
+
+
+def test_golden_ssd_replay(eng):
+    z = load("b100_ssd_replay.npz")
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    sim = eng.engine.Simulator(net, 2)
+    sim.set_state(z["init"])
+    rp = eng.engine.Replay(z["ints"], z["dbls"], "cuda")
+    hist = sim.ssd(int(z["iters"]), float(z["p"]), z["tgt_nodes"], replay=rp)
+    assert np.array_equal(hist.cpu().numpy(), z["hist"].sum(0))
+    used = rp.used.cpu().numpy()
+    assert np.array_equal(used[:, 0], [z["ints"].shape[1]] * 2) and np.array_equal(used[:, 1], [z["dbls"].shape[1]] * 2)
+
+
+# ------------------------------------------------------------------------------------------------ Philox mode vs oracle
+def _nets(eng, which):
+    if which == "tt":
+        rng = np.random.default_rng(5)
+        n = 70
+        pbn_data = []
+        for i in range(n):
+            k = int(rng.integers(0, 6))
+            mask = np.zeros(n, bool)
+            mask[rng.choice(n, size=k, replace=False)] = True
+            f1, f2 = rng.integers(0, 2, 2**k), rng.integers(0, 2, 2**k)
+            c = float(rng.uniform(0.05, 0.95))
+            pbn_data.append((mask, (c * f1 + (1 - c) * f2).reshape([2] * k), f"n{i}", k == 0))
+        return eng.engine.Network(eng.compiler.compile_pbn_data(pbn_data)), orc.net_from_pbn_data(pbn_data)
+    sets, ids = orc.load_bittner(which)
+    return eng.engine.Network(eng.compiler.load_bittner(which)), orc.net_from_predictor_sets(sets, ids)
+
+
+@pytest.mark.parametrize("which", ["28_15_median", "100_5_kmeans", "200_5_kmeans", "70_5_kmeans", "tt"])
+@pytest.mark.parametrize("sync", [False, True])
+def test_philox_rollout_matches_oracle(eng, which, sync):
+    net, onet = _nets(eng, which)
+    B, steps, seed, env0 = 1000, (7 if sync else 300), 1234, 5_000_000_000
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=env0)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0, B=B), env0=env0)
+    assert np.array_equal(_state_np(sim), ost)
+    sim.rollout(steps, sync=sync)
+    od = orc.Draws(seed=seed, epoch=1, B=B)
+    orc.rollout(onet, ost, steps, od, sync=sync, env0=env0)
+    assert np.array_equal(_state_np(sim), ost)
+
+
+def test_philox_split_invariance(eng):
+    """env e's stream is keyed by its global id: two half-ranges == one full range (the multi-GPU contract)."""
+    net, _ = _nets(eng, "100_5_kmeans")
+    full = eng.engine.Simulator(net, 512, seed=9, env0=100)
+    full.rand_state(); full.rollout(200)
+    halves = []
+    for k in range(2):
+        h = eng.engine.Simulator(net, 256, seed=9, env0=100 + 256 * k)
+        h.rand_state(); h.rollout(200)
+        halves.append(_state_np(h))
+    assert np.array_equal(_state_np(full), np.concatenate(halves))
+
+
+def _fixture_atts(n, rng, n_att=4, care=5):
+    atts = []
+    for a in range(n_att):
+        cubes = []
+        for _ in range(1 + a % 2):
+            c = ["*"] * n
+            for i in rng.choice(n, size=care, replace=False):
+                c[i] = int(rng.integers(0, 2))
+            cubes.append(tuple(c))
+        atts.append(cubes)
+    return atts
+
+
+@pytest.mark.parametrize("kind", ["target", "target_force", "multi", "multi_list"])
+def test_philox_env_step_matches_oracle(eng, kind):
+    net, onet = _nets(eng, "100_5_kmeans")
+    rng = np.random.default_rng(3)
+    n, B, seed = net.n, 2048, 77
+    atts = _fixture_atts(n, rng)
+    ek = eng.abi.ENV_TARGET if kind.startswith("target") else eng.abi.ENV_MULTI
+    kw = dict(attractors=atts, horizon=7, max_inner=200, force=(kind == "target_force"), dedup=(kind != "multi_list"))
+    env = eng.engine.EnvImage(net, ek, **kw)
+    oenv = orc.Env(orc.ENV_TARGET if kind.startswith("target") else orc.ENV_MULTI, n, attractors=atts, horizon=7,
+                   max_inner=200, force=int(kind == "target_force"), dedup=int(kind != "multi_list"))
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost = np.zeros((B, n), np.uint8)
+    ons, ota = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    otgt = np.zeros((B, n), np.uint8)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0), target_state=otgt)
+    assert np.array_equal(_state_np(sim), ost) and np.array_equal(sim.target_att.cpu().numpy(), ota)
+    assert np.array_equal(sim.unpack(sim.target_state).cpu().numpy(), otgt)
+    K = 1 if kind.startswith("target") else 3
+    for t in range(12):
+        act = rng.integers(0, n + 1, size=(B, K)).astype(np.int32)
+        if K == 3:
+            dup = rng.random(B) < 0.3
+            act[dup, 2] = act[dup, 0]
+        sim.env_step(env, torch.from_numpy(act))
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + 2 * t))
+        assert np.array_equal(_state_np(sim), ost), t
+        assert np.array_equal(sim.unpack(sim.obs_state).cpu().numpy(), obs), t
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.terminated.cpu().numpy(), term)
+        assert np.array_equal(sim.truncated.cpu().numpy(), trunc) and np.array_equal(sim.inner.cpu().numpy(), inner)
+        done = (term | trunc).astype(np.uint8)
+        sim.env_reset(env, mask=torch.from_numpy(done))
+        orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=2 + 2 * t), mask=done)
+        assert np.array_equal(_state_np(sim), ost) and np.array_equal(sim.n_steps.cpu().numpy(), ons)
+
+
+@pytest.mark.parametrize("kind", ["pbn", "pbcn", "pbn_sd", "pbcn_sd", "pbcn_sd_write"])
+def test_philox_tt_env_step_matches_oracle(eng, kind):
+    net, onet = _nets(eng, "tt")
+    rng = np.random.default_rng(4)
+    n, B, seed = net.n, 1500, 5
+    atts = [[tuple(int(v) for v in rng.integers(0, 2, n)) for _ in range(1 + a)] for a in range(3)]
+    targets = [atts[2][0], tuple(int(v) for v in rng.integers(0, 2, n))]
+    kmap = {"pbn": (eng.abi.ENV_PBN, orc.ENV_PBN), "pbcn": (eng.abi.ENV_PBCN, orc.ENV_PBCN),
+            "pbn_sd": (eng.abi.ENV_PBN_SD, orc.ENV_PBN_SD), "pbcn_sd": (eng.abi.ENV_PBCN_SD, orc.ENV_PBCN_SD),
+            "pbcn_sd_write": (eng.abi.ENV_PBCN_SD, orc.ENV_PBCN_SD)}
+    M = 3
+    cw = kind == "pbcn_sd_write"
+    env = eng.engine.EnvImage(net, kmap[kind][0], attractors=atts, targets=targets, n_control=M, control_write=cw,
+                              successful_reward=10, wrong_attractor_cost=2)
+    oenv = orc.Env(kmap[kind][1], n, attractors=atts, targets=targets, n_control=M, control_write=int(cw),
+                   successful_reward=10, wrong_attractor_cost=2)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost = np.zeros((B, n), np.uint8)
+    ons, ota = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    assert np.array_equal(_state_np(sim), ost)
+    # random states make rewards non-trivial: plant targets/attractor states into a third of the envs
+    plant = rng.random(B) < 0.3
+    ost[plant] = np.array(targets[0], np.uint8)
+    sim.set_state(ost)
+    for t in range(6):
+        if kind in ("pbn", "pbcn"):
+            act = rng.integers(0, n, size=(B, 1))
+        elif kind == "pbn_sd":
+            act = np.stack([rng.integers(0, n + 1, B), rng.integers(1, 20, B)], 1)
+        else:
+            act = np.concatenate([rng.integers(1, 20, (B, 1)), rng.integers(0, 2, (B, M))], 1)
+        act = act.astype(np.int32)
+        sim.env_step(env, torch.from_numpy(act))
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + t))
+        assert np.array_equal(_state_np(sim), ost), t
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.terminated.cpu().numpy(), term)
+        assert np.array_equal(sim.inner.cpu().numpy(), inner)
+
+
+@pytest.mark.parametrize("which,p", [("100_5_kmeans", 0.01), ("28_15_median", 0.05), ("200_5_kmeans", 0.0), ("tt", 1.0)])
+def test_philox_ssd_matches_oracle(eng, which, p):
+    net, onet = _nets(eng, which)
+    B, iters, seed = 3000, 400, 99
+    tgt = np.array([0, 1, 2, 3, 4, 5, 6], np.int32) if which != "tt" else np.array([3, 41, 69, 7], np.int32)
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=17)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0), env0=17)
+    hist = sim.ssd(iters, p, tgt)
+    ohist = orc.ssd(onet, None, ost, iters, p, tgt, orc.Draws(seed=seed, epoch=1), env0=17)
+    assert hist.sum().item() == B * iters
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
+    assert np.array_equal(_state_np(sim), ost)
+
+
+def test_philox_ssd_with_attractor_loop(eng):
+    net, onet = _nets(eng, "28_15_median")
+    rng = np.random.default_rng(8)
+    atts = _fixture_atts(net.n, rng, care=3)
+    env = eng.engine.EnvImage(net, eng.abi.ENV_TARGET, attractors=atts, max_inner=50)
+    oenv = orc.Env(orc.ENV_TARGET, net.n, attractors=atts, max_inner=50)
+    B, iters, seed = 1024, 100, 3
+    tgt = np.arange(9, dtype=np.int32)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0))
+    hist = sim.ssd(iters, 0.01, tgt, env=env)
+    ohist = orc.ssd(onet, oenv, ost, iters, 0.01, tgt, orc.Draws(seed=seed, epoch=1))
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
+    assert np.array_equal(_state_np(sim), ost)
+
+
+def test_large_g_uses_global_histogram(eng):
+    net, onet = _nets(eng, "100_5_kmeans")
+    B, iters, seed = 512, 64, 21
+    tgt = np.arange(14, dtype=np.int32)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0))
+    hist = sim.ssd(iters, 0.01, tgt)
+    ohist = orc.ssd(onet, None, ost, iters, 0.01, tgt, orc.Draws(seed=seed, epoch=1))
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
+
+
+def test_replay_lockstep_256_envs(eng):
+    """256 envs x 1000 async updates under synthetic replayed draws: CUDA (float64 compares) == oracle."""
+    net, onet = _nets(eng, "28_15_median")
+    rng = np.random.default_rng(2)
+    B, steps, n = 256, 1000, net.n
+    ints = rng.integers(0, n, size=(B, steps)).astype(np.int32)
+    dbls = rng.random((B, steps))
+    st0 = rng.integers(0, 2, size=(B, n)).astype(np.uint8)
+    sim = eng.engine.Simulator(net, B)
+    sim.set_state(st0)
+    sim.rollout(steps, replay=eng.engine.Replay(ints, dbls, "cuda"))
+    ost = st0.copy()
+    orc.rollout(onet, ost, steps, orc.Draws(ints=ints, dbls=dbls))
+    assert np.array_equal(_state_np(sim), ost)
+
+
+def test_pack_unpack_roundtrip(eng):
+    net, _ = _nets(eng, "200_5_kmeans")
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2, size=(777, net.n)).astype(np.uint8)
+    sim = eng.engine.Simulator(net, 777)
+    sim.set_state(bits)
+    assert np.array_equal(_state_np(sim), bits)
