@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — Bittner-100 env-steps/s on N B200s (SSD estimation workload), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--gpus N] ...                # CPU arm: the oracle port on all host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # N > 1: one rank per GPU, NCCL
+
+Workload (BASELINE.json configs[2]): gym-PBN/Bittner-100 steady-state-distribution estimate —
+2^20 chains per GPU, each step advances every chain by 9600 SSD iterations (histogram the 7 target genes,
+flip each gene w.p. 0.01, one asynchronous node update = one env.step(0) under the all-attracting fixture);
+one step = the 1.0e10-iteration estimate of configs[2].  value = SSD iterations (= env-steps) per second over all ranks.
+N > 1: chains are sharded by global chain id (weak scaling), the 128-bucket histogram is all-reduced (NCCL) each step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "gym-pbn-stac_b200"))
+
+NET_NAME = "100_5_kmeans"
+TARGET_NODES = list(range(7))  # genes 234237..130057 are nodes 0..6 of the shipped set (pbn_target.py:447)
+CHAINS_PER_GPU = 1 << 20
+ITERS_PER_STEP = 9600  # 2^20 chains x 9600 = 1.0066e10 iterations: one step = one full SSD estimate per GPU
+FLIP_P = 0.01
+SEED = 0
+METRIC = "bittner100_env_steps_per_s"
+UNIT = "env-steps/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"gym-PBN/Bittner-100 SSD estimation ({NET_NAME}): {CHAINS_PER_GPU} chains/GPU x {ITERS_PER_STEP} "
+                    f"iterations/step, bit_flip_prob={FLIP_P}, 7 target genes (128 buckets), async update, all-attracting",
+        "chains_per_gpu": CHAINS_PER_GPU, "iters_per_step": ITERS_PER_STEP, "update": "async",
+        "rng": "philox4x32-10", "parallelism": f"env-sharded x{n_gpus}", "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_sample(target_seconds=12.0):
+    """Times the oracle port (oracle/pbn_oracle.c, OpenMP over chains) on a bounded sample of the same workload."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as orc
+
+    sets, ids = orc.load_bittner(NET_NAME)
+    net = orc.net_from_predictor_sets(sets, ids)
+    cores = orc.num_threads()
+    tgt = np.array(TARGET_NODES, np.int32)
+    # calibrate, then size the sample (chains) for ~target_seconds at the workload's own chain length
+    chains = 256 * cores
+    st = orc.rand_state(net, chains, orc.Draws(seed=SEED, epoch=0))
+    t0 = time.perf_counter()
+    orc.ssd(net, None, st, 200, FLIP_P, tgt, orc.Draws(seed=SEED, epoch=1))
+    rate = chains * 200 / (time.perf_counter() - t0)
+    iters = ITERS_PER_STEP
+    chains = int(max(cores, min(CHAINS_PER_GPU, rate * target_seconds / iters)))
+    st = orc.rand_state(net, chains, orc.Draws(seed=SEED, epoch=0))
+    t0 = time.perf_counter()
+    orc.ssd(net, None, st, iters, FLIP_P, tgt, orc.Draws(seed=SEED, epoch=2))
+    dt = time.perf_counter() - t0
+    return {"value": chains * iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{chains} chains x {iters} iterations of the same Bittner-100 SSD workload, oracle/pbn_oracle.c "
+                      f"(C restatement of the pure-Python reference, Philox draws, OpenMP), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step = max(2.0, min(12.0, 60.0 / (steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(per_step)
+    vals, t0 = [], time.perf_counter()
+    last = None
+    for _ in range(steps):
+        last = cpu_sample(per_step)
+        vals.append(last["value"])
+    value = float(np.mean(vals))
+    last["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": (time.perf_counter() - t0) * 1e3 / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": last,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def load_inst_per_iter():
+    """Executed thread-level instructions per SSD iteration, measured once with ncu (profiles/); used for the
+    issue-rate roofline.  Falls back to a static estimate if the profile summary is absent."""
+    p = ROOT / "profiles" / "ssd_inst_per_iter.json"
+    if p.exists():
+        return json.loads(p.read_text())
+    return {"thread_inst_per_iter": None, "source": "absent"}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from gym_PBN.b200 import compiler, engine
+    from gym_PBN.utils.eval import ssd_histogram_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    net = engine.Network(compiler.load_bittner(NET_NAME), device=dev)
+    sim = engine.Simulator(net, CHAINS_PER_GPU, seed=SEED, env0=rank * CHAINS_PER_GPU)
+    sim.rand_state()
+    tgt = np.array(TARGET_NODES, np.int32)
+    hist = torch.zeros(128, dtype=torch.int64, device=dev)
+    total = torch.zeros(128, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        hist.zero_()
+        sim.ssd(ITERS_PER_STEP, FLIP_P, tgt, hist=hist)
+        if world > 1:
+            dist.all_reduce(hist)
+        total.add_(hist)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- device-resident timing (value): per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = sim.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        hist.zero_()
+        kev[k][0].record()
+        sim.ssd(ITERS_PER_STEP, FLIP_P, tgt, hist=hist)
+        kev[k][1].record()
+        if world > 1:
+            dist.all_reduce(hist)
+        total.add_(hist)
+        ev[k][1].record()
+    barrier()
+    launches = (sim.launches - launches0)
+    t_steps = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3 / args.steps
+    clocks = sampler.stop()
+    tt = torch.tensor([t_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_steps = float(tt.item())
+    units = float(CHAINS_PER_GPU) * ITERS_PER_STEP * args.steps * world
+    value = units / t_steps
+
+    # ---- end-to-end through the public API with HOST buffers (start states up, histogram back), every step
+    n = net.n
+    host_states = torch.randint(0, 2, (CHAINS_PER_GPU, n), dtype=torch.uint8).pin_memory()
+    ssd_histogram_host(net, host_states, ITERS_PER_STEP, FLIP_P, tgt, seed=SEED, env0=rank * CHAINS_PER_GPU)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        h = ssd_histogram_host(net, host_states, ITERS_PER_STEP, FLIP_P, tgt, seed=SEED + k, env0=rank * CHAINS_PER_GPU,
+                               distributed=(world > 1))
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = units / float(te.item())
+    assert int(h.sum()) == CHAINS_PER_GPU * ITERS_PER_STEP * world
+
+    # sanity: every iteration of every chain was histogrammed
+    tot = total.clone()
+    assert int(tot.sum().item()) == (max(3, args.warmup) + args.steps) * CHAINS_PER_GPU * ITERS_PER_STEP * world
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_ssd): instruction issue, not HBM (near-zero DRAM traffic by design)
+        alu_peak, _ = engine.issue_peak(0, 4000)      # thread-level INT ops/s, measured on this GPU now
+        philox_peak, _ = engine.issue_peak(1, 4000)   # Philox4x32-10 blocks/s, measured on this GPU now
+        per_launch_iters = float(CHAINS_PER_GPU) * ITERS_PER_STEP
+        ipi = load_inst_per_iter()
+        tipi = ipi.get("thread_inst_per_iter")
+        achieved = per_launch_iters * tipi / t_kernel if tipi else None
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        state_bytes = per_launch_iters * (8 * 2 + 8)  # 8W read + 8 written per micro-step, W = 2 (uint64 words)
+        hbm_alg = (2 * net.w32 * 4 * CHAINS_PER_GPU + 128 * 8)  # bytes that must cross HBM per launch: state in + out, histogram
+        roofline = {
+            "bound": "issue", "kernel": "k_ssd<PRED,PHILOX>",
+            "achieved": achieved / 1e9 if achieved else None, "peak": alu_peak / 1e9, "unit": "G thread-instr/s",
+            "frac": (achieved / alu_peak) if achieved else None,
+            "peak_source": "pbn_issue_peak(0): dependency-free LOP3+IADD3 chains, measured in this run",
+            "thread_inst_per_iter": tipi, "inst_source": ipi.get("source"),
+            "kernel_ms": t_kernel * 1e3,
+            "iters_per_s_kernel": per_launch_iters / t_kernel,
+            "philox_blocks_per_s_peak": philox_peak,
+            "state_bytes_per_s": state_bytes / t_kernel,
+            "traffic": ipi.get("dram_bytes_per_launch"),
+            "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg / t_kernel / 1e9, "peak_gbs": hbm_peak,
+                    "frac": hbm_alg / t_kernel / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        }
+        cpu = cpu_sample(12.0)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": t_steps * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic", "config": workload_config(n_gpus), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_states.numel()),
+                        "d2h_bytes_per_step": 128 * 8,
+                        "api": "gym_PBN.utils.eval.ssd_histogram_host (pinned uint8 start states up, uint64 histogram back)"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "node_updates_per_s": value, "ssd_1e10_seconds": 1.0e10 / value}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

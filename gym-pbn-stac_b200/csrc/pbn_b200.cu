@@ -12,8 +12,6 @@
 
 #include "pbn_device.cuh"
 
-#define PBN_BLOCK 256
-
 // ----------------------------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) {
@@ -222,24 +220,24 @@ static DrawView make_draws(const PbnDraws *d) {
 }
 
 // ----------------------------------------------------------------------------------------------- K1 rollout
-template <int NET, int MODE>
+template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, u32 *state, long long B, long long env0,
                                                        long long steps, int sync) {
     unsigned char *blob = smem_raw;
     u32 *sst = reinterpret_cast<u32 *>(smem_raw + nv.blob_bytes);
     stage(blob, nv.blob, nv.blob_bytes);
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    Col st{sst + threadIdx.x, (int)blockDim.x};
-    Col tmp{sst + nv.w32 * blockDim.x + threadIdx.x, (int)blockDim.x};
+    const long long e = (long long)blockIdx.x * PBN_BLOCK + threadIdx.x;
+    Col st{sst + threadIdx.x};
+    Col tmp{sst + nv.w32 * PBN_BLOCK + threadIdx.x};
     if (e < B) load_state(st, state, B, e, nv.w32);
     __syncthreads();
     if (e >= B) return;
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
     if (sync)
-        for (long long t = 0; t < steps; t++) sync_step<NET, MODE>(nv, blob, st, tmp, d);
+        for (long long t = 0; t < steps; t++) sync_step<NET, MODE, TQ>(nv, blob, st, tmp, d);
     else
-        for (long long t = 0; t < steps; t++) micro_step<NET, MODE>(nv, blob, st, d);
+        for (long long t = 0; t < steps; t++) micro_step<NET, MODE, TQ>(nv, blob, st, d);
     store_state(st, state, B, e, nv.w32);
     d.done(dv, e);
 }
@@ -272,8 +270,8 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int w32 = nv.w32;
-    Col st{sst + threadIdx.x, (int)blockDim.x};
-    Col ob{sst + w32 * blockDim.x + threadIdx.x, (int)blockDim.x};
+    Col st{sst + threadIdx.x};
+    Col ob{sst + w32 * PBN_BLOCK + threadIdx.x};
     if (e < B) load_state(st, state, B, e, w32);
     __syncthreads();
     if (e >= B) return;
@@ -435,63 +433,82 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rand_state(NetView nv, DrawView d
 struct SsdParams {
     int g;
     int smem_hist;  // 1: per-block shared histogram (g <= 12), 0: global atomics
-    float inv;      // 1/log2(1-p); < 0 = flips disabled
+    int fast_t0;    // >= 0: the targets are nodes t0, t0+1, .. t0+g-1 inside one state word (bucket = bit-reversed field)
+    float inv;      // 1/log2(1-p) <= 0; a value > 0 means flips disabled (p == 0)
     double p;
     short tgt[24];
 };
 
-template <int NET, int MODE>
-__global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, int has_env, DrawView dv, SsdParams sp, u32 *state,
-                                                   long long chains, long long env0, long long iters,
+// bucket = target-node bits, first target = most significant (pbn_target.py:383-391)
+__device__ __forceinline__ int ssd_bucket(const SsdParams &sp, const u32 *s_tgt, const Col &st) {
+    if (sp.fast_t0 >= 0) {
+        u32 field = (*st.wp((u32)sp.fast_t0) >> (sp.fast_t0 & 31)) << (32 - sp.g);
+        return (int)__brev(field);
+    }
+    int b = 0;
+    for (int k = 0; k < sp.g; k++) b = (b << 1) | (int)st.bit(s_tgt[k]);
+    return b;
+}
+
+template <int NET, int MODE, int TQ, bool HAS_ENV>
+__global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, DrawView dv, SsdParams sp, u32 *state,
+                                                   long long chains, long long env0, int iters,
                                                    unsigned long long *hist) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
-    const int img_bytes = has_env ? ev.img_bytes : 0;
-    u32 *shist = reinterpret_cast<u32 *>(img + img_bytes);
+    const int img_bytes = HAS_ENV ? ev.img_bytes : 0;
+    u32 *s_tgt = reinterpret_cast<u32 *>(img + img_bytes);
+    u32 *shist = s_tgt + 32;
     const int nb = 1 << sp.g;
     u32 *sst = shist + (sp.smem_hist ? nb : 0);
     stage(blob, nv.blob, nv.blob_bytes);
-    if (has_env) stage(img, ev.img, ev.img_bytes);
+    if (HAS_ENV) stage(img, ev.img, ev.img_bytes);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 24; k++) s_tgt[k] = (u32)sp.tgt[k];  // static indices: read straight from the parameter bank
+    }
     if (sp.smem_hist)
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) shist[b] = 0;
+        for (int b = threadIdx.x; b < nb; b += PBN_BLOCK) shist[b] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int w32 = nv.w32, n = nv.n;
-    Col st{sst + threadIdx.x, (int)blockDim.x};
+    const long long e = (long long)blockIdx.x * PBN_BLOCK + threadIdx.x;
+    const int w32 = nv.w32;
+    const u32 n = (u32)nv.n;
+    Col st{sst + threadIdx.x};
     if (e < chains) load_state(st, state, chains, e, w32);
     __syncthreads();
     if (e < chains) {
         Draw<MODE> d;
         d.init(dv, e, env0 + e);
+        const float inv = sp.inv;
+        const bool flips = inv <= 0.f;
         u32 pos = 0;
-        if constexpr (MODE == PBN_DRAW_PHILOX) pos = sp.inv < 0.f ? 0xFFFFFFFFu : geom_gap(d.next(), sp.inv);
-        int cur = -1;
+        if constexpr (MODE == PBN_DRAW_PHILOX) pos = flips ? geom_gap(d.next(), inv) : 0xFFFFFFFFu;
+        int cur = ssd_bucket(sp, s_tgt, st);
         u32 run = 0;
-        for (long long t = 0; t < iters; t++) {
-            int b = 0;
-            for (int k = 0; k < sp.g; k++) b = (b << 1) | (int)st.bit(sp.tgt[k]);  // MSB-first, pbn_target.py:383-391
+        for (int t = 0; t < iters; t++) {
+            const int b = ssd_bucket(sp, s_tgt, st);
             if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
-                if (run) {
-                    if (sp.smem_hist) atomicAdd(&shist[cur], run);
-                    else atomicAdd(&hist[cur], (unsigned long long)run);
-                }
+                if (sp.smem_hist) atomicAdd(&shist[cur], run);
+                else atomicAdd(&hist[cur], (unsigned long long)run);
                 cur = b; run = 0;
             }
             run++;
             if constexpr (MODE == PBN_DRAW_REPLAY) {
-                for (int j = 0; j < n; j++)
+                for (u32 j = 0; j < n; j++)
                     if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
             } else {
-                if (sp.inv >= 0.f) {
-                    while (pos < (u32)n) { st.flip((int)pos); pos += 1u + geom_gap(d.next(), sp.inv); }
-                    pos -= (u32)n;
+                if (flips) {
+                    while (pos < n) { st.flip(pos); pos += 1u + geom_gap(d.next(), inv); }
+                    pos -= n;
                 }
             }
-            micro_step<NET, MODE>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
-            if (has_env && !ev.force) {
-                int in = 1;
-                while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE>(nv, blob, st, d); in++; }
+            micro_step<NET, MODE, TQ>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
+            if constexpr (HAS_ENV) {
+                if (!ev.force) {
+                    int in = 1;
+                    while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE, TQ>(nv, blob, st, d); in++; }
+                }
             }
         }
         if (run) {
@@ -503,7 +520,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, int h
     }
     if (sp.smem_hist) {
         __syncthreads();
-        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        for (int b = threadIdx.x; b < nb; b += PBN_BLOCK)
             if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
     }
 }
@@ -581,14 +598,17 @@ static int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PBN_OK;
 }
-static inline int block_for(long long B) { return B >= PBN_BLOCK ? PBN_BLOCK : (int)(((B + 31) / 32) * 32); }
+static inline int block_for(long long) { return PBN_BLOCK; }  // columns use a compile-time word stride of PBN_BLOCK
 
-#define DISPATCH(NETKIND, MODE, CALL)                                                       \
-    do {                                                                                    \
-        if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX); } \
-        else if ((NETKIND) == PBN_NET_PRED) { CALL(PBN_NET_PRED, PBN_DRAW_REPLAY); }        \
-        else if ((MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_TT, PBN_DRAW_PHILOX); }          \
-        else { CALL(PBN_NET_TT, PBN_DRAW_REPLAY); }                                         \
+// kernels are instantiated per (network kind, draw source, threshold quads TQ); TQ = 1 covers predictor sets with
+// up to 5 predictors per node (every shipped *_5_* set), TQ = 0 reads the count at run time
+#define DISPATCH(NETKIND, MODE, TS, CALL)                                                        \
+    do {                                                                                         \
+        if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX && (TS) == 4) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX, 1); } \
+        else if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX, 0); }         \
+        else if ((NETKIND) == PBN_NET_PRED) { CALL(PBN_NET_PRED, PBN_DRAW_REPLAY, 0); }          \
+        else if ((MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_TT, PBN_DRAW_PHILOX, 0); }            \
+        else { CALL(PBN_NET_TT, PBN_DRAW_REPLAY, 0); }                                           \
     } while (0)
 
 static int check_draws(const PbnDraws *d) {
@@ -609,10 +629,10 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const size_t smem = (size_t)nv.blob_bytes + (size_t)2 * nv.w32 * block * 4;
     cudaStream_t s = (cudaStream_t)stream;
-#define CALL(NK, MD)                                                               \
-    if (int rc = set_smem(k_rollout<NK, MD>, smem)) return rc;                     \
-    k_rollout<NK, MD><<<grid, block, smem, s>>>(nv, dv, state, B, env0, steps, sync)
-    DISPATCH(nv.kind, dv.mode, CALL);
+#define CALL(NK, MD, TQ)                                                           \
+    if (int rc = set_smem(k_rollout<NK, MD, TQ>, smem)) return rc;                 \
+    k_rollout<NK, MD, TQ><<<grid, block, smem, s>>>(nv, dv, state, B, env0, steps, sync)
+    DISPATCH(nv.kind, dv.mode, nv.ts, CALL);
 #undef CALL
     CK(cudaGetLastError());
     return PBN_OK;
@@ -636,11 +656,11 @@ extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
     cudaStream_t s = (cudaStream_t)stream;
-#define CALL(NK, MD)                                                                                              \
+#define CALL(NK, MD, TQ)                                                                                          \
     if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                                   \
     k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state,   \
                                                  reward, terminated, truncated, inner_steps, B, env0)
-    DISPATCH(nv.kind, dv.mode, CALL);
+    DISPATCH(nv.kind, dv.mode, 0, CALL);
 #undef CALL
     CK(cudaGetLastError());
     return PBN_OK;
@@ -694,24 +714,35 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     const DrawView dv = make_draws(draws);
     SsdParams sp;
     sp.g = g; sp.p = p; sp.smem_hist = g <= 12;
-    sp.inv = p <= 0 ? -1.0f : (p >= 1 ? 0.0f : (float)(1.0 / std::log2(1.0 - p)));
+    sp.inv = p <= 0 ? 1.0f : (p >= 1 ? 0.0f : (float)(1.0 / std::log2(1.0 - p)));
+    memset(sp.tgt, 0, sizeof sp.tgt);
     for (int k = 0; k < g; k++) {
         if (tgt[k] < 0 || tgt[k] >= nv.n) return fail(PBN_ERR_ARG, "target node out of range");
         sp.tgt[k] = (short)tgt[k];
     }
+    // fast bucket path: targets are consecutive ascending nodes inside one 32-bit state word
+    sp.fast_t0 = tgt[0];
+    for (int k = 1; k < g; k++)
+        if (tgt[k] != tgt[0] + k) sp.fast_t0 = -1;
+    if (sp.fast_t0 >= 0 && (tgt[0] >> 5) != ((tgt[0] + g - 1) >> 5)) sp.fast_t0 = -1;
     const int block = block_for(chains);
-    if (sp.smem_hist && (double)iters * block >= 4294967296.0) return fail(PBN_ERR_ARG, "iters too large for one launch; split the estimate");
+    if (iters >= (1LL << 31) || (sp.smem_hist && (double)iters * block >= 4294967296.0))
+        return fail(PBN_ERR_ARG, "iters too large for one launch; split the estimate");
     const unsigned grid = (unsigned)((chains + block - 1) / block);
     EnvView ev;
     memset(&ev, 0, sizeof ev);
     if (env) ev = env->v;
-    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4;
+    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4;
     cudaStream_t s = (cudaStream_t)stream;
-#define CALL(NK, MD)                                                                                      \
-    if (int rc = set_smem(k_ssd<NK, MD>, smem)) return rc;                                                \
-    k_ssd<NK, MD><<<grid, block, smem, s>>>(nv, ev, env ? 1 : 0, dv, sp, state, chains, env0, iters,      \
-                                            (unsigned long long *)hist)
-    DISPATCH(nv.kind, dv.mode, CALL);
+#define CALL(NK, MD, TQ)                                                                                  \
+    if (env) {                                                                                            \
+        if (int rc = set_smem(k_ssd<NK, MD, TQ, true>, smem)) return rc;                                  \
+        k_ssd<NK, MD, TQ, true><<<grid, block, smem, s>>>(nv, ev, dv, sp, state, chains, env0, (int)iters, (unsigned long long *)hist);  \
+    } else {                                                                                              \
+        if (int rc = set_smem(k_ssd<NK, MD, TQ, false>, smem)) return rc;                                 \
+        k_ssd<NK, MD, TQ, false><<<grid, block, smem, s>>>(nv, ev, dv, sp, state, chains, env0, (int)iters, (unsigned long long *)hist); \
+    }
+    DISPATCH(nv.kind, dv.mode, nv.ts, CALL);
 #undef CALL
     CK(cudaGetLastError());
     return PBN_OK;

@@ -154,30 +154,37 @@ __device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
 }
 
 // ----------------------------------------------------------------------------------------------- state column
+#define PBN_BLOCK 256  // every kernel runs 256-thread blocks, so a column's word stride is a compile-time constant
 struct Col {
-    u32 *s;      // &state_smem[threadIdx.x]
-    int stride;  // blockDim.x
+    u32 *s;  // &state_smem[threadIdx.x]; word w of this thread lives at s[w * PBN_BLOCK]
+    static constexpr int stride = PBN_BLOCK;
+    __device__ __forceinline__ u32 *wp(u32 pos) const {  // address of the word holding bit `pos`: (pos & ~31) * (4*256/32) bytes on
+        return reinterpret_cast<u32 *>(reinterpret_cast<char *>(s) + ((pos & ~31u) << 5));
+    }
     __device__ __forceinline__ u32 word(int w) const { return s[w * stride]; }
     __device__ __forceinline__ void set_word(int w, u32 v) const { s[w * stride] = v; }
-    __device__ __forceinline__ u32 bit(int pos) const { return (s[(pos >> 5) * stride] >> (pos & 31)) & 1u; }
-    __device__ __forceinline__ void flip(int pos) const { s[(pos >> 5) * stride] ^= 1u << (pos & 31); }
-    __device__ __forceinline__ void put(int pos, u32 v) const {
-        u32 *p = s + (pos >> 5) * stride;
-        u32 m = 1u << (pos & 31);
+    __device__ __forceinline__ u32 bit(u32 pos) const { return (*wp(pos) >> (pos & 31u)) & 1u; }
+    __device__ __forceinline__ void flip(u32 pos) const { *wp(pos) ^= 1u << (pos & 31u); }
+    __device__ __forceinline__ void put(u32 pos, u32 v) const {
+        u32 *p = wp(pos);
+        u32 m = 1u << (pos & 31u);
         *p = (*p & ~m) | (v ? m : 0u);
     }
 };
 
 // ----------------------------------------------------------------------------------------------- node updates
 // bittner/base.py:89-119 Node.Predstep.  `blob` is the shared-memory copy of the network image.
-template <int MODE>
+// TQ = number of threshold quads per node known at compile time (1: up to 5 predictors), 0 = read nv.ts at run time
+template <int MODE, int TQ>
 __device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
     int j;
     if constexpr (MODE == PBN_DRAW_PHILOX) {
         u32 r = d.next() >> 1;
-        const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * (nv.ts >> 2);
+        const int nq = TQ > 0 ? TQ : (nv.ts >> 2);
+        const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * nq;
         j = 0;
-        for (int q = 0; q < (nv.ts >> 2); q++) {
+#pragma unroll
+        for (int q = 0; q < nq; q++) {
             uint4 t = thr[q];
             j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
         }
@@ -210,27 +217,27 @@ __device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *b
     }
 }
 
-template <int NET, int MODE>
+template <int NET, int MODE, int TQ>
 __device__ __forceinline__ u32 node_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
-    if constexpr (NET == PBN_NET_PRED) return pred_next<MODE>(nv, blob, st, i, d);
+    if constexpr (NET == PBN_NET_PRED) return pred_next<MODE, TQ>(nv, blob, st, i, d);
     else return tt_next<MODE>(nv, blob, st, i, d);
 }
 
 // one asynchronous update: PBN.step common/pbn.py:88-92 / PBCN.step common/pbcn.py:59-61 / Graph.step base.py:306-312
-template <int NET, int MODE>
+template <int NET, int MODE, int TQ = 0>
 __device__ __forceinline__ void micro_step(const NetView &nv, const unsigned char *blob, const Col &st, Draw<MODE> &d) {
     int i = d.randint(nv.first, nv.n - nv.first);
-    u32 v = node_next<NET, MODE>(nv, blob, st, i, d);
+    u32 v = node_next<NET, MODE, TQ>(nv, blob, st, i, d);
     st.put(i, v);
 }
 
 // Graph.synch_step (perturbations off) base.py:300-303: every node from the OLD state, in node order
-template <int NET, int MODE>
+template <int NET, int MODE, int TQ = 0>
 __device__ __forceinline__ void sync_step(const NetView &nv, const unsigned char *blob, const Col &st, const Col &tmp,
                                           Draw<MODE> &d) {
     u32 acc = 0;
     for (int i = 0; i < nv.n; i++) {
-        acc |= node_next<NET, MODE>(nv, blob, st, i, d) << (i & 31);
+        acc |= node_next<NET, MODE, TQ>(nv, blob, st, i, d) << (i & 31);
         if ((i & 31) == 31 || i == nv.n - 1) { tmp.set_word(i >> 5, acc); acc = 0; }
     }
     for (int w = 0; w < nv.w32; w++) st.set_word(w, tmp.word(w));

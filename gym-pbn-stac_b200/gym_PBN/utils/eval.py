@@ -1,0 +1,107 @@
+"""Steady-state-distribution (SSD) estimation on the GPU.
+
+Drop-in for the reference's `compute_ssd_hist` (gym_PBN/utils/eval.py:20-72) and its worker `_ssd_run` (:76-103):
+`resets` independent chains, each `iters // resets` iterations of  histogram(target-gene pattern) -> flip every gene
+w.p. bit_flip_prob -> env.step(0).  Here every chain is one GPU thread of the K3 kernel (pbn_ssd), the per-chain
+float32 histograms + np.mean of the reference become one exact uint64 histogram, and with torch.distributed
+initialised the chains are sharded over ranks and the histogram is all-reduced (NCCL).
+"""
+import itertools
+
+import numpy as np
+import torch
+
+from gym_PBN.b200 import dist as pdist
+from gym_PBN.b200 import engine
+
+MAX_ITERS_PER_LAUNCH = 1 << 22  # keeps a block's 32-bit shared-memory bucket counts far from overflow
+
+
+def _run_chains(net, sim, iters, p, tgt, env_image, hist):
+    left = int(iters)
+    while left > 0:
+        chunk = min(left, MAX_ITERS_PER_LAUNCH)
+        sim.ssd(chunk, p, tgt, env=env_image, hist=hist)
+        left -= chunk
+    return hist
+
+
+def ssd_histogram_host(net, start_states, iters, bit_flip_prob, tgt_nodes, env_image=None, seed=0, env0=0, distributed=False):
+    """Visit histogram of len(start_states) chains x `iters` iterations, HOST in / HOST out.
+
+    start_states: uint8/bool [chains][N] host array or (pinned) CPU tensor — what env.render() hands out.
+    Returns a NumPy int64 [2^g] histogram (summed over ranks when distributed=True)."""
+    st = start_states if torch.is_tensor(start_states) else torch.from_numpy(np.ascontiguousarray(start_states, dtype=np.uint8))
+    chains = st.shape[0]
+    sim = engine.Simulator(net, chains, seed=seed, env0=env0)
+    dev_states = st.to(net.device, non_blocking=True)
+    sim.set_state(dev_states)
+    tgt = np.ascontiguousarray(tgt_nodes, np.int32)
+    hist = torch.zeros(1 << len(tgt), dtype=torch.int64, device=net.device)
+    _run_chains(net, sim, iters, bit_flip_prob, tgt, env_image, hist)
+    if distributed:
+        pdist.allreduce_sum_(hist)
+    return hist.cpu().numpy()
+
+
+def ssd_histogram(env, iters, chains, bit_flip_prob=0.01, seed=None, distributed=True):
+    """Device-side estimate for one of our envs: chains start from env.reset() states (or uniform random states when the
+    env has no attractor list), sharded over ranks by global chain id.  Returns (int64 device histogram, total iterations)."""
+    net = env.network
+    start, stop = pdist.shard_range(chains) if distributed else (0, chains)
+    local = stop - start
+    seed = env._next_seed() if seed is None else seed
+    sim = engine.Simulator(net, max(local, 1), seed=seed, env0=start)
+    image = env.env_image
+    if local > 0:
+        if image is not None and image.n_att >= 2:
+            sim.env_reset(image)       # env.reset() per chain (eval.py:78)
+        else:
+            sim.rand_state()           # no attractors known: Graph.genRandState
+    tgt = np.asarray(env.target_node_indices, np.int32)
+    hist = torch.zeros(1 << len(tgt), dtype=torch.int64, device=net.device)
+    per_chain = int(iters)
+    if local > 0:
+        _run_chains(net, sim, per_chain, bit_flip_prob, tgt, image, hist)
+    if distributed:
+        pdist.allreduce_sum_(hist)
+    return hist, per_chain * chains
+
+
+def compute_ssd_hist(env, model=None, iters=1_200_000, resets=300, bit_flip_prob=0.01, multiprocess=True, seed=None):
+    """Reference signature (utils/eval.py:20-27).  Returns (DataFrame indexed '0..0'..'1..1' MSB-first with column
+    "Value", figure-or-None).  `multiprocess` is accepted for compatibility; parallelism here is the GPU's."""
+    SSD_N, SSD_RESETS = int(iters), int(resets)
+    assert bit_flip_prob >= 0 and bit_flip_prob <= 1, "Invalid Bit Flip Probability value."
+    assert SSD_RESETS > 0, "Invalid resets value."
+    assert SSD_N > 0, "Invalid iterations value."
+    assert SSD_N // SSD_RESETS, "Resets does not divide the iterations."
+    if model is not None:
+        raise NotImplementedError("policy-in-the-loop SSD (model.predict per step) is not on the GPU path yet")
+    g = len(env.target_nodes)
+    hist, total = ssd_histogram(env, SSD_N // SSD_RESETS, SSD_RESETS, bit_flip_prob, seed=seed)
+    ssd = hist.cpu().numpy().astype(np.float64) / float(total)
+    states = ["".join(str(b) for b in bits) for bits in itertools.product([0, 1], repeat=g)]
+    try:
+        import pandas as pd
+
+        ret = pd.DataFrame(list(ssd), index=states, columns=["Value"])
+    except Exception:  # pandas is optional plumbing
+        ret = {"index": states, "Value": ssd}
+    return ret, visualize_ssd(ret, getattr(env, "name", None))
+
+
+def visualize_ssd(ssd_frame, env_name):
+    """Bar chart of the estimate when plotly is installed (reference: utils/eval.py:139-157); None otherwise."""
+    try:
+        import plotly.express as px
+
+        fig = px.bar(ssd_frame, x=list(ssd_frame.index), y="Value", title=f"SSD for {env_name}")
+        return fig
+    except Exception:
+        return None
+
+
+def total_variation(p, q):
+    p, q = np.asarray(p, np.float64), np.asarray(q, np.float64)
+    return 0.5 * float(np.abs(p / p.sum() - q / q.sum()).sum())

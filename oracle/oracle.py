@@ -250,3 +250,10 @@ def load_bittner(name):
     sets = pickle.load(open(DATA / f"predictor_sets_{name}.pkl", "rb"))
     ids = json.load(open(DATA / "node_ids.json"))[name]["node_ids"]
     return sets, ids
+
+
+def geom_law(p, kmax=4096):
+    """counts[k] = number of the 2^23 equally likely inputs that orc_geom maps to gap k (last bin = tail)."""
+    counts = np.zeros(kmax, np.int64)
+    lib().orc_geom_law(C.c_double(p), _p(counts), C.c_int(kmax))
+    return counts

@@ -170,7 +170,7 @@ uint32_t orc_geom(uint32_t r, float inv) {
     return (uint32_t)g;
 }
 float orc_geom_inv(double p) { /* host helper shared by tests: 1/log2(1-p) as float */
-    if (p <= 0) return -1.0f;  /* sentinel: flips disabled */
+    if (p <= 0) return 1.0f;  /* sentinel (> 0): flips disabled; every valid value is <= 0 */
     if (p >= 1) return 0.0f;
     return (float)(1.0 / log2(1.0 - p));
 }
@@ -427,7 +427,7 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
         Dr d; dr_init(&d, dr, e, env0 + e);
         uint8_t *st = state + e * n;
         int64_t pos = 0;
-        if (d.mode == ORC_PHILOX) pos = inv < 0 ? INT64_MAX / 2 : (int64_t)orc_geom(dr_u32(&d), inv);
+        if (d.mode == ORC_PHILOX) pos = inv > 0 ? INT64_MAX / 2 : (int64_t)orc_geom(dr_u32(&d), inv);
         for (int64_t t = 0; t < iters; t++) {
             int64_t b = 0;
             for (int k = 0; k < g; k++) b = (b << 1) | st[tgt_nodes[k]];
@@ -447,6 +447,15 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
     for (int t = 0; t < nthreads; t++) for (int64_t b = 0; b < nb; b++) hist[b] += priv[t * nb + b];
     free(priv);
     return 0;
+}
+
+/* exact law of orc_geom: counts[k] = #{x in [0, 2^23) : G(x << 9) == k} for k < kmax (last bin collects the tail) */
+void orc_geom_law(double p, int64_t *counts, int kmax) {
+    const float inv = orc_geom_inv(p);
+    for (uint32_t x = 0; x < (1u << 23); x++) {
+        uint32_t g = orc_geom(x << 9, inv);
+        counts[g < (uint32_t)kmax ? g : (uint32_t)kmax - 1]++;
+    }
 }
 
 int orc_num_threads(void) {

@@ -378,3 +378,50 @@ def test_pack_unpack_roundtrip(eng):
     sim = eng.engine.Simulator(net, 777)
     sim.set_state(bits)
     assert np.array_equal(_state_np(sim), bits)
+
+
+# ------------------------------------------------------------------------------------------------ statistics (Philox mode)
+def _tv(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+
+@pytest.mark.parametrize("p,T", [(0.01, 50), (0.3, 5)])
+def test_philox_flip_rate_gpu(eng, p, T):
+    """Identity dynamics: only the perturbation changes bits, so P(bit = 1 after T) = (1 - (1-2p)^T) / 2."""
+    n, B = 100, 50000
+    data = []
+    for i in range(n):
+        mask = np.zeros(n, bool)
+        mask[i] = True
+        data.append((mask, np.array([0.0, 1.0]), f"n{i}", False))
+    net = eng.engine.Network(eng.compiler.compile_pbn_data(data))
+    sim = eng.engine.Simulator(net, B, seed=3)
+    hist = sim.ssd(T, p, np.arange(3, dtype=np.int32))
+    assert int(hist.sum()) == B * T
+    st = _state_np(sim)
+    expect = (1 - (1 - 2 * p) ** T) / 2
+    sigma = np.sqrt(expect * (1 - expect) / (B * n))
+    assert abs(st.mean() - expect) <= 5 * sigma
+    assert np.abs(st.mean(0) - expect).max() <= 6 * np.sqrt(expect * (1 - expect) / B)
+
+
+def test_ssd_total_variation_vs_reference_gpu(eng):
+    """Independent RNG: TV(GPU estimate, reference estimate) <= 3 x TV between two reference runs, at the reference's
+    default budget (1.2 M iterations over 300 chains).  A 100x larger GPU estimate must sit within the same bound."""
+    z = load("b100_ssd_long.npz")
+    ref_a, ref_b = z["ssd"]
+    floor = _tv(ref_a, ref_b)
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    tgt = np.arange(7, dtype=np.int32)
+    chains, iters = int(z["resets"]), int(z["iters"]) // int(z["resets"])
+    sim = eng.engine.Simulator(net, chains, seed=5)
+    sim.rand_state()
+    hist = sim.ssd(iters, float(z["p"]), tgt).cpu().numpy()
+    assert _tv(hist, ref_a) <= 3 * floor and _tv(hist, ref_b) <= 3 * floor
+    big = eng.engine.Simulator(net, 30000, seed=6)
+    big.rand_state()
+    hb = big.ssd(iters, float(z["p"]), tgt).cpu().numpy()
+    pooled = ref_a + ref_b
+    assert _tv(hb, pooled) <= 3 * floor
+    print("TV floor", floor, "gpu-vs-refA", _tv(hist, ref_a), "gpu(big)-vs-pooled", _tv(hb, pooled))

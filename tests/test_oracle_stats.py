@@ -1,0 +1,110 @@
+"""CPU: statistical checks of the PHILOX-mode semantics (the stream the CUDA kernels use), on the oracle.
+
+Replay mode is pinned bit-for-bit to the reference (test_oracle_golden.py).  Philox mode replaces the reference's
+float64 draws by 31-bit integer thresholds and its N Bernoulli(p) perturbation draws per iteration by a
+geometric-skip process; these tests check that those substitutions keep the reference's laws."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from golden_util import load
+
+
+@pytest.mark.parametrize("p", [0.01, 0.05, 0.3])
+def test_geometric_gap_law(p):
+    """Enumerate all 2^23 inputs of the gap function: P(G = k) must be (1-p)^k p."""
+    kmax = 6000
+    counts = orc.geom_law(p, kmax).astype(np.float64)
+    emp = counts / counts.sum()
+    k = np.arange(kmax)
+    pmf = (1 - p) ** k * p
+    pmf[-1] = (1 - p) ** (kmax - 1)
+    assert np.abs(emp - pmf).max() < 4e-6          # 2^-23 input quantisation + polynomial error
+    assert 0.5 * np.abs(emp - pmf).sum() < 2e-4    # total variation of the whole law
+    mean = (emp * k).sum()
+    assert abs(mean - (1 - p) / p) < 2e-3 * (1 - p) / p
+    # per-position flip probability implied by the renewal process = 1 / (1 + E[G])
+    assert abs(1.0 / (1.0 + mean) - p) < 2e-3 * p
+
+
+def _identity_net(n):
+    data = []
+    for i in range(n):
+        mask = np.zeros(n, bool)
+        mask[i] = True
+        data.append((mask, np.array([0.0, 1.0]), f"n{i}", False))
+    return orc.net_from_pbn_data(data)
+
+
+@pytest.mark.parametrize("p,T", [(0.01, 50), (0.05, 7), (1.0, 3), (0.0, 9)])
+def test_philox_flip_rate(p, T):
+    """Identity dynamics: only the perturbation changes bits, so P(bit = 1 after T) = (1 - (1-2p)^T) / 2."""
+    n, B = 100, 20000
+    net = _identity_net(n)
+    st = np.zeros((B, n), np.uint8)
+    hist = orc.ssd(net, None, st, T, p, np.arange(3, dtype=np.int32), orc.Draws(seed=3, epoch=0))
+    assert hist.sum() == B * T
+    expect = (1 - (1 - 2 * p) ** T) / 2
+    got = st.mean()
+    sigma = np.sqrt(max(expect * (1 - expect), 1e-12) / (B * n))
+    assert abs(got - expect) <= 5 * sigma + 1e-12, (got, expect)
+    # no position is favoured (flip positions uniform over the n nodes)
+    per_node = st.mean(0)
+    assert np.abs(per_node - expect).max() <= 6 * np.sqrt(max(expect * (1 - expect), 1e-12) / B) + 1e-12
+
+
+def test_philox_transition_frequencies():
+    """chi-square: empirical P(next = 1 | inputs) of a truth-table node under Philox thresholds == its table."""
+    n = 4
+    probs = np.array([0.0, 0.123, 0.5, 0.7, 0.3, 0.999, 1.0, 0.05])
+    data = []
+    for i in range(n):
+        mask = np.zeros(n, bool)
+        if i == 3:
+            mask[:3] = True
+            data.append((mask, probs.reshape(2, 2, 2), "x", False))
+        else:
+            mask[i] = True
+            data.append((mask, np.array([0.0, 1.0]), f"n{i}", False))
+    net = orc.net_from_pbn_data(data)
+    B = 400_000
+    rng = np.random.default_rng(0)
+    st = rng.integers(0, 2, size=(B, n)).astype(np.uint8)
+    before = st.copy()
+    ints = np.full((B, 1), 3, np.int32)  # not used in philox mode; node choice is random in [1, n)
+    orc.rollout(net, st, 1, orc.Draws(seed=11, epoch=0))
+    changed_other = (st[:, :3] != before[:, :3]).any()
+    assert not changed_other
+    idx = before[:, 0] * 4 + before[:, 1] * 2 + before[:, 2]
+    # node 3 is picked w.p. 1/3; when not picked it keeps its value. Use only rows where it could be inferred:
+    # P(x'=1 | idx, x) = (1/3) * P[idx] + (2/3) * x
+    for k in range(8):
+        for x in (0, 1):
+            sel = (idx == k) & (before[:, 3] == x)
+            m = sel.sum()
+            expect = probs[k] / 3 + 2 * x / 3
+            got = st[sel, 3].mean()
+            sigma = np.sqrt(max(expect * (1 - expect), 1e-9) / m)
+            assert abs(got - expect) < 5 * sigma + 1e-9, (k, x, got, expect)
+
+
+def tv(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+
+def test_ssd_total_variation_vs_reference():
+    """SSD of Bittner-100 under independent RNG: TV(oracle-Philox, reference) <= 3 x TV(reference run A, run B)
+    at the reference's default budget (1.2 M iterations, 300 chains; utils/eval.py:23-25)."""
+    z = load("b100_ssd_long.npz")
+    ref_a, ref_b = z["ssd"]
+    floor = tv(ref_a, ref_b)
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    chains, iters = int(z["resets"]), int(z["iters"]) // int(z["resets"])
+    st = orc.rand_state(net, chains, orc.Draws(seed=5, epoch=0))
+    hist = orc.ssd(net, None, st, iters, float(z["p"]), np.arange(7, dtype=np.int32), orc.Draws(seed=5, epoch=1))
+    got = tv(hist, ref_a)
+    print("TV floor (ref vs ref)", floor, "TV oracle vs ref", got)
+    assert 0.002 < floor < 0.1
+    assert got <= 3 * floor
