@@ -1,0 +1,162 @@
+"""PBNVectorEnv — `num_envs` lockstep copies of one gym_PBN env on one GPU, everything resident on the device.
+
+The reference has no vectorised env (one Python object per env).  Here one CUDA launch performs
+`env.step` for every env: interventions, update(s) until attracting (capped), reward / terminated / truncated; a second
+launch resets the envs that finished.  Observations, rewards and flags are torch tensors on the device, owned by the
+env and overwritten by the next `step` (clone them to keep them).
+
+Multi-GPU: one process per GPU; pass `global_num_envs` and the env ids are sharded over ranks
+(gym_PBN.b200.dist.shard_range).  Every env's Philox stream is keyed by its GLOBAL id, so an N-rank job reproduces
+the 1-rank job bit for bit; `stats.reduced()` all-reduces the episode statistics.
+"""
+import numpy as np
+import torch
+
+from . import abi, dist as pdist, engine
+
+_KIND_OF = {"PBNEnv": abi.ENV_PBN, "PBCNEnv": abi.ENV_PBCN, "PBNSampledDataEnv": abi.ENV_PBN_SD,
+            "PBCNSampledDataEnv": abi.ENV_PBCN_SD}
+
+
+def _family(env):
+    from gym_PBN.envs.pbn_env import PBNEnv
+    from gym_PBN.envs.pbn_target import PBNTargetEnv
+    from gym_PBN.envs.pbn_target_multi import PBNTargetMultiEnv
+
+    if isinstance(env, PBNTargetMultiEnv):
+        return "multi"
+    if isinstance(env, PBNTargetEnv):
+        return "target"
+    if isinstance(env, PBNEnv):
+        return "pbn"
+    raise TypeError(f"cannot vectorise {type(env).__name__}")
+
+
+class PBNVectorEnv:
+    def __init__(self, env, num_envs=None, seed=0, autoreset=True, global_num_envs=None, obs="bits", dedup=True,
+                 max_inner_steps=None, force=False, action_slots=3):
+        env = getattr(env, "unwrapped", env)
+        self.env = env
+        self.family = _family(env)
+        self.network = env.network
+        self.device = self.network.device
+        if global_num_envs is not None:
+            start, stop = pdist.shard_range(global_num_envs)
+            num_envs, env0 = stop - start, start
+        else:
+            env0 = 0
+        if not num_envs or num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.num_envs, self.env0 = int(num_envs), int(env0)
+        self.autoreset, self.obs_mode = bool(autoreset), obs
+        self.n = self.network.n
+        self.sim = engine.Simulator(self.network, self.num_envs, seed=seed, env0=self.env0)
+        self.single_observation_space = env.observation_space
+        self.single_action_space = env.action_space
+        self.max_inner_steps = int(max_inner_steps if max_inner_steps is not None else getattr(env, "max_inner_steps", 1))
+        self.action_slots = action_slots
+        if self.family == "pbn":
+            kind = next(v for k, v in _KIND_OF.items() if k in [c.__name__ for c in type(env).__mro__])
+            self.image = engine.EnvImage(
+                self.network, kind, attractors=[sorted(a) for a in env.all_attractors], targets=sorted(env.target_nodes),
+                n_control=getattr(env.PBN, "M", 0), control_write=getattr(env.PBN, "control_mode", "stac") == "write",
+                successful_reward=env.successful_reward, wrong_attractor_cost=env.wrong_attractor_cost)
+            self.action_width = {abi.ENV_PBN: 1, abi.ENV_PBCN: 1, abi.ENV_PBN_SD: 2}.get(kind, 1 + getattr(env.PBN, "M", 0))
+            self.horizon = 0
+        else:
+            atts = env.all_attractors or [[("*",) * self.n], [("*",) * self.n]]  # all-attracting fixture
+            self.image = engine.EnvImage(
+                self.network, abi.ENV_TARGET if self.family == "target" else abi.ENV_MULTI, attractors=atts,
+                horizon=env.horizon, max_inner=self.max_inner_steps, force=force, dedup=dedup)
+            self.action_width = 1 if self.family == "target" else action_slots
+            self.horizon = env.horizon
+        self.stats = pdist.EpisodeStats(self.device)
+        self.ep_return = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        self.ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self.final_obs = torch.zeros_like(self.sim.state)
+        self._needs_reset = True
+
+    # ---- observations -----------------------------------------------------------------------------------------
+    def _obs(self, planes):
+        return planes if self.obs_mode == "packed" else self.sim.unpack(planes)
+
+    @property
+    def state(self):
+        """Live packed state planes int32 [W32][num_envs] (bit i&31 of word i>>5 = node i)."""
+        return self.sim.state
+
+    # ---- API --------------------------------------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.sim.reseed(seed)
+        self.sim.env_reset(self.image)
+        self.ep_return.zero_()
+        self.ep_len.zero_()
+        self._needs_reset = False
+        info = {"target_attractor": self.sim.target_att, "target_state_packed": self.sim.target_state}
+        return self._obs(self.sim.state), info
+
+    def step(self, actions):
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions))
+        actions = actions.to(self.device, dtype=torch.int32, non_blocking=True).reshape(self.num_envs, -1)
+        if actions.shape[1] != self.action_width:
+            raise ValueError(f"actions must have shape [{self.num_envs}, {self.action_width}]")
+        sim = self.sim
+        sim.env_step(self.image, actions)
+        done = (sim.terminated | sim.truncated)
+        self.ep_return += sim.reward
+        self.ep_len += 1
+        n_done = done.sum()
+        st = self.stats.v
+        st[0] += n_done
+        st[1] += (self.ep_return * done).sum()
+        st[2] += (self.ep_len * done).sum()
+        st[3] += sim.terminated.sum()
+        st[4] += (sim.inner >= self.max_inner_steps).sum() if self.family != "pbn" else 0
+        st[5] += self.num_envs
+        obs_planes = sim.obs_state
+        info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state}
+        if self.autoreset:
+            self.final_obs.copy_(sim.obs_state)
+            info["final_obs_packed"] = self.final_obs
+            sim.env_reset(self.image, mask=done)
+            keep = (1 - done).to(torch.int64)
+            self.ep_return *= keep
+            self.ep_len *= keep.to(torch.int32)
+            # envs that were reset observe their new state; the others keep the step's observation
+            obs_planes = torch.where(done.bool().unsqueeze(0), sim.state, sim.obs_state)
+        return self._obs(obs_planes), sim.reward, sim.terminated.bool(), sim.truncated.bool(), info
+
+    def step_host(self, actions_host):
+        """Host in / host out convenience (pinned staging): NumPy actions -> NumPy (obs, reward, terminated, truncated)."""
+        a = torch.as_tensor(np.ascontiguousarray(actions_host, dtype=np.int32))
+        obs, r, te, tr, _ = self.step(a.pin_memory().to(self.device, non_blocking=True))
+        return obs.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+
+    def close(self):
+        pass
+
+    # ---- checkpoint -------------------------------------------------------------------------------------------
+    def state_dict(self):
+        s = self.sim
+        return {"state": s.state.clone(), "n_steps": s.n_steps.clone(), "target_att": s.target_att.clone(),
+                "target_state": s.target_state.clone(), "seed": s.seed, "epoch": s.epoch, "env0": s.env0,
+                "ep_return": self.ep_return.clone(), "ep_len": self.ep_len.clone(), "stats": self.stats.v.clone()}
+
+    def load_state_dict(self, d):
+        s = self.sim
+        s.state.copy_(d["state"]); s.n_steps.copy_(d["n_steps"]); s.target_att.copy_(d["target_att"])
+        s.target_state.copy_(d["target_state"])
+        s.seed, s.epoch, s.env0 = int(d["seed"]), int(d["epoch"]), int(d["env0"])
+        self.ep_return.copy_(d["ep_return"]); self.ep_len.copy_(d["ep_len"]); self.stats.v.copy_(d["stats"])
+        self._needs_reset = False
+
+
+def make_vec(id, num_envs, vec_kwargs=None, **env_kwargs):
+    import gym_PBN
+
+    env = gym_PBN.make(id, **env_kwargs)
+    return PBNVectorEnv(env, num_envs, **(vec_kwargs or {}))

@@ -1,0 +1,158 @@
+"""Truth-table PBN core on the GPU (reference: gym_PBN/envs/common/pbn.py).
+
+`PBN.step()` is the reference's ASYNCHRONOUS update — one node i ~ U{1..N-1} is redrawn from its truth table
+(common/pbn.py:88-92; node 0 is never updated) — executed by the CUDA rollout kernel on a bit-packed device state.
+`state` is exposed as a NumPy bool array like the reference's attribute (a copy: assign to `pbn.state` or call
+`reset` to change it).  The exhaustive state-transition graph (`print_STG`, common/pbn.py:132-216) stays on the host:
+it is O(2^N), constructor-time only, and feeds attractor lists, not the step path.
+"""
+import numpy as np
+
+from gym_PBN.b200 import compiler, engine
+from gym_PBN.utils import booleanize
+from gym_PBN.utils.converters import logic_funcs_to_PBN_data
+
+from .node import Node
+
+
+class PBN:
+    def __init__(self, PBN_data=None, logic_func_data=None, goal_config=None, device=None, seed=None):
+        if PBN_data is not None and len(PBN_data) != 0:
+            data = list(PBN_data)
+        else:
+            if logic_func_data is None:
+                raise ValueError("PBN needs PBN_data or logic_func_data")
+            data = logic_funcs_to_PBN_data(*logic_func_data)
+        self._init_from_pbn_data(data, device, seed)
+        if goal_config is not None:
+            self.target_nodes = goal_config["target_nodes"]
+
+    def _init_from_pbn_data(self, data, device=None, seed=None):
+        self.spec = compiler.compile_pbn_data(data)
+        self.N = self.spec.n
+        self.nodes = np.empty(self.N, dtype=object)
+        for i, node in enumerate(data):
+            mask, table, name, ctrl = compiler._split_node(node)
+            self.nodes[i] = Node(mask, table, i, self.spec.names[i], ctrl)
+        self.network = engine.Network(self.spec, device=device)
+        self.sim = engine.Simulator(self.network, 1, seed=0 if seed is None else seed)
+        self.PBN_graph = None
+        self.STG = None
+
+    # ---- state -----------------------------------------------------------------------------------------
+    @property
+    def state(self):
+        return self.sim.unpack()[0].cpu().numpy().astype(bool)
+
+    @state.setter
+    def state(self, value):
+        self.sim.set_state(np.asarray(value, dtype=np.uint8).reshape(1, self.N))
+
+    def reset(self, state=None):
+        """Set the state (random when None); node 0 is forced to 0 exactly as common/pbn.py:77 does."""
+        if state is None:
+            new = np.random.rand(self.N) > 0.5
+        else:
+            if len(state) != self.N:
+                raise Exception(
+                    f"The length of the state given ({len(state)}) is different from the PBN size ({self.N})."
+                )
+            new = np.array(state, dtype=bool)
+        new[0] = False
+        self.state = new
+        return new
+
+    def flip(self, index):
+        i = int(np.asarray(index).reshape(-1)[0])
+        if not 0 <= i < self.N:
+            raise IndexError(f"index {i} is out of bounds for a PBN of {self.N} nodes")
+        self.sim.state[i >> 5, 0] ^= _bit32(i & 31)
+
+    def step(self, steps=1):
+        """`steps` asynchronous node updates in one kernel launch."""
+        self.sim.rollout(steps)
+
+    # ---- descriptive helpers ---------------------------------------------------------------------------
+    def name_nodes(self, names):
+        for node, name in zip(self.nodes, names):
+            node.name = name
+
+    def get_node_by_name(self, name):
+        for node in self.nodes:
+            if node.name == name:
+                return node
+        raise Exception(f'Node with name "{name}" not found.')
+
+    def print_functions(self):
+        return [node.function for node in self.nodes]
+
+    def print_PBN(self, no_cache=False):
+        import networkx as nx
+
+        if self.PBN_graph is None or no_cache:
+            G = nx.DiGraph()
+            G.add_nodes_from(node.name for node in self.nodes)
+            for node in self.nodes:
+                G.add_edges_from((src.name, node.name) for src in self.nodes[node.input_mask])
+            self.PBN_graph = G
+        return self.PBN_graph
+
+    def async_successors(self, state):
+        """[(next_state bool[N], probability-of-node-being-1)] of the asynchronous dynamics, all N nodes considered
+        (common/pbn.py:186-197: an edge exists when the node can change value)."""
+        out = []
+        state = np.asarray(state, dtype=bool)
+        for i, node in enumerate(self.nodes):
+            p = node.get_next_value_prob(state)
+            if (p > 0.0 and not state[i]) or (p < 1.0 and state[i]):
+                nxt = state.copy()
+                nxt[i] = not state[i]
+                out.append((nxt, p))
+        return out
+
+    def print_STG(self, no_cache=False):
+        """networkx DiGraph over all 2^N states, node labels = str(int array) as in the reference."""
+        import networkx as nx
+
+        if self.STG is None or no_cache:
+            G = nx.DiGraph()
+            for idx in range(2**self.N):
+                s = booleanize(idx, self.N)
+                label = str(s.astype(int))
+                G.add_node(label)
+                G.add_weighted_edges_from((label, str(n.astype(int)), p) for n, p in self.async_successors(s))
+            self.STG = G
+        return self.STG
+
+    def attractors(self, max_nodes=22):
+        """Terminal strongly connected components of the asynchronous STG, as a list of sets of state tuples
+        (what PBNEnv.compute_attractors obtains from networkx, pbn_env.py:238-255).  Host-side, N <= max_nodes."""
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import connected_components
+
+        if self.N > max_nodes:
+            raise ValueError(f"exhaustive attractor search is O(2^N); N={self.N} > {max_nodes}")
+        S = 2**self.N
+        weights = 1 << np.arange(self.N - 1, -1, -1)
+        rows, cols = [], []
+        for idx in range(S):
+            s = booleanize(idx, self.N)
+            for nxt, _p in self.async_successors(s):
+                rows.append(idx)
+                cols.append(int(nxt.astype(np.int64) @ weights))
+        A = csr_matrix((np.ones(len(rows), np.int8), (rows, cols)), shape=(S, S))
+        ncomp, label = connected_components(A, directed=True, connection="strong")
+        leaves = np.ones(ncomp, bool)
+        for r, c in zip(rows, cols):
+            if label[r] != label[c]:
+                leaves[label[r]] = False
+        out = []
+        for comp in np.nonzero(leaves)[0]:
+            members = np.nonzero(label == comp)[0]
+            out.append({tuple(int(b) for b in booleanize(int(m), self.N)) for m in members})
+        return out
+
+
+def _bit32(b):
+    """1 << b as a signed 32-bit Python int (the device planes are int32 tensors)."""
+    return (1 << b) if b < 31 else -(1 << 31)

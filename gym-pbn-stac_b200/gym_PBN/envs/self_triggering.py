@@ -1,0 +1,104 @@
+"""Self-triggering envs (reference: gym_PBN/envs/self_triggering.py): a macro action is (primitive, prob in 1..10);
+after every primitive step it stops with probability prob/10 (or at i == T), inner rewards are discounted by gamma**i.
+SURVEY.md §8f ranks these "next"; they are served by looping the single-step kernel from the host, with the stop draw
+taken from Python's `random.uniform` exactly where the reference draws it (self_triggering.py:79,181).
+"""
+import random
+
+import numpy as np
+
+from gym_PBN.b200 import abi, engine
+from gym_PBN.b200.gym_compat import spaces
+from gym_PBN.utils import booleanize
+
+from ._device import state_to_idx
+from .pbcn_env import PBCNEnv
+from .pbn_env import PBNEnv
+
+
+class PBNSelfTriggeringEnv(PBNEnv):
+    def __init__(self, render_mode="human", render_no_cache=False, PBN_data=None, logic_func_data=None, name=None,
+                 goal_config=None, reward_config=None, gamma=0.99, T=None, device=None, seed=None):
+        super().__init__(render_mode, render_no_cache, PBN_data, logic_func_data, name, goal_config, reward_config,
+                         device=device, seed=seed)
+        self.gamma = gamma
+        self.T = T
+        self.primitive_action_space = spaces.Discrete(self.PBN.N + 1)
+        self.prob_space = spaces.Discrete(10, start=1)
+        self.action_space = spaces.Tuple((self.primitive_action_space, self.prob_space))
+        self.discrete_action_space = spaces.Discrete(self.primitive_action_space.n * self.prob_space.n)
+
+    def _one_step_image(self):  # PBNSampledDataEnv's body with interval = 1: flip(a-1), update, PBNEnv reward
+        return self._image("st1", lambda: engine.EnvImage(
+            self.network, abi.ENV_PBN_SD, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states()))
+
+    def step(self, action):
+        if not self.action_space.contains(action):
+            raise Exception(f"Invalid action {action}, not in action space.")
+        control_action, prob = action
+        prob = prob / 10
+        total_reward, i, end = 0, 0, False
+        terminated = truncated = False
+        while not end:
+            reward, terminated, truncated, _ = self._run_step(self._one_step_image(), [int(control_action), 1])
+            total_reward += (self.gamma**i) * reward
+            i += 1
+            end = random.uniform(0, 1) <= prob or i == self.T
+        observation = self.PBN.state
+        return observation, total_reward, terminated, truncated, {
+            "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}
+
+
+class PBCNSelfTriggeringEnv(PBCNEnv):
+    def __init__(self, render_mode="human", render_no_cache=False, PBN_data=None, logic_func_data=None, name=None,
+                 goal_config=None, reward_config=None, gamma=0.99, T=None, device=None, seed=None, control="stac"):
+        super().__init__(render_mode, render_no_cache, PBN_data, logic_func_data, name, goal_config, reward_config,
+                         device=device, seed=seed, control=control)
+        self.gamma = gamma
+        self.T = T
+        self.primitive_action_space = spaces.MultiBinary(self.PBN.M)
+        self.primitive_action_space.dtype = bool
+        self.prob_space = spaces.Discrete(10, start=1)
+        self.action_space = spaces.Tuple((self.primitive_action_space, self.prob_space))
+        self.discrete_action_space = spaces.Discrete((2**self.PBN.M) * self.prob_space.n)
+        # "Reward hardcode" of the reference (self_triggering.py:134-137)
+        self.successful_reward = 1
+        self.wrong_attractor_cost = 1
+        self.action_cost = 1
+        self._invalidate_images()
+
+    def _idx_to_macro_action(self, i):
+        m = self.PBN.M
+        return booleanize(i % (2**m), m).tolist(), i // (2**m) + 1
+
+    def _one_step_image(self):  # PBCNSampledDataEnv's body with interval = 1: reward - 1 (time step cost)
+        return self._image("st1", lambda: engine.EnvImage(
+            self.network, abi.ENV_PBCN_SD, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states(),
+            n_control=self.PBN.M, control_write=self.PBN.control_mode == "write",
+            successful_reward=self.successful_reward, wrong_attractor_cost=self.wrong_attractor_cost))
+
+    def step(self, action):
+        if action is None:
+            raise Exception("You need to provide a macro action with either `macro_action` or `macro_action_discrete`.")
+        if np.isscalar(action):
+            if not self.discrete_action_space.contains(action):
+                raise Exception(f"Invalid action {action}, not in action space.")
+            action = self._idx_to_macro_action(int(action))
+        if type(action[1]) is float:
+            action = (action[0], int(action[1] * 10))
+        if not self.action_space.contains(action):
+            raise Exception(f"Invalid action {action}, not in action space.")
+        control_action, prob = action
+        prob = prob / 10
+        control = [int(bool(c)) for c in np.asarray(control_action).reshape(-1)]
+        self.PBN.apply_control(control)
+        total_reward, i, end = 0, 0, False
+        terminated = truncated = False
+        while not end:
+            reward, terminated, truncated, _ = self._run_step(self._one_step_image(), [1] + control)
+            total_reward += (self.gamma**i) * reward
+            i += 1
+            end = random.uniform(0, 1) <= prob or i == self.T
+        observation = self.PBN.state
+        return observation, total_reward, terminated, truncated, {
+            "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}

@@ -1,0 +1,262 @@
+"""GPU: the drop-in gymnasium surface (gym_PBN.make / env classes) and the batched PBNVectorEnv.
+
+Single-env classes are checked for API shape, return types and — by driving the same kernels with the oracle in
+Philox mode from the same seed/epoch — for exact values.  The VectorEnv is checked against the oracle step by step."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle as orc  # noqa: E402
+from golden_util import cubes_to_attractors, load  # noqa: E402
+
+EX5 = (["u", "x1", "x2", "x3", "x4"],
+       [[], [("not x2 and not x4", 1)], [("not x4 and not u and (x2 or x3)", 1)],
+        [("not x2 and not x4 and x1", 0.7), ("False", 0.3)], [("not x2 and not x3", 1)]])
+GOAL = {"target_nodes": {(0, 0, 0, 0, 1)}, "target": {(0, 0, 0, 0, 1)},
+        "all_attractors": [{(0, 0, 1, 0, 0)}, {(0, 0, 0, 0, 1)}]}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_make_pbn_v0_example_network():
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/PBN-v0", logic_func_data=EX5, goal_config=dict(GOAL))
+    # attractors of the example network: computed exhaustively in the constructor
+    assert sorted(map(sorted, env.all_attractors)) == [[(0, 0, 0, 0, 1)], [(0, 0, 1, 0, 0)]]
+    obs, info = env.reset(seed=0)
+    assert obs.dtype == bool and obs.shape == (5,) and tuple(obs) in env.attracting_states
+    assert info["observation_idx"] == int("".join(str(int(b)) for b in obs), 2)
+    seen_term = False
+    for t in range(300):
+        a = t % 5
+        obs, r, term, trunc, info = env.step(a)
+        assert isinstance(r, int) and isinstance(term, bool) and trunc is False and obs[0] == 0
+        hit = tuple(int(b) for b in obs) in env.target_nodes
+        assert term == hit and r == (20 if hit else -4 - (a != 0))
+        if term:
+            seen_term = True
+            obs, info = env.reset()
+    assert seen_term
+    with pytest.raises(Exception):
+        env.step(5)
+
+
+def test_readme_style_pbcn_example_runs():
+    """example.py:19-44 (`gym.make("gym-PBN/PBCN-v0", ...)` with README-style goal_config and action [1]) fails in the
+    reference with KeyError('target_nodes'); here it runs."""
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/PBCN-v0", logic_func_data=EX5,
+                       goal_config={"all_attractors": [{(0, 0, 0, 0, 1)}, {(0, 0, 1, 0, 0)}], "target": {(0, 0, 0, 0, 1)}})
+    assert env.PBN.M == 1 and env.action_space.n == 1 and env.discrete_action_space.n == 2
+    env.reset(seed=3)
+    for _ in range(10):
+        obs, r, term, trunc, info = env.step([1])
+        assert r in (env.successful_reward, -env.wrong_attractor_cost, 0)
+        if term:
+            break
+
+
+def test_sampled_data_env_variable_intervals():
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/PBCN-sampled-data-v0", logic_func_data=EX5, goal_config=dict(GOAL), T=8)
+    env.reset(seed=1)
+    obs, r, term, trunc, info = env.step(([True], 5))
+    assert info["interval"] == 5 and isinstance(r, int)
+    obs, r, term, trunc, info = env.step(2 * 3 + 1)  # flat index -> ([True], 4)
+    assert info["interval"] == 4 and info["control_action"] == [True]
+    with pytest.raises(Exception):
+        env.step(([True], 9))
+    env2 = gym_PBN.make("gym-PBN/PBN-sampled-data-v0", logic_func_data=EX5, goal_config=dict(GOAL), T=8)
+    env2.reset(seed=1)
+    obs, r, term, trunc, info = env2.step((2, 3))
+    assert info["interval"] == 2
+
+
+def test_self_triggering_envs_run():
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/PBN-self-triggering-v0", logic_func_data=EX5, goal_config=dict(GOAL), T=6)
+    env.reset(seed=2)
+    obs, r, term, trunc, info = env.step((1, 3))
+    assert 1 <= info["interval"] <= 6
+    env = gym_PBN.make("gym-PBN/PBCN-self-triggering-v0", logic_func_data=EX5, goal_config=dict(GOAL), T=6)
+    env.reset(seed=2)
+    obs, r, term, trunc, info = env.step(([False], 10))
+    assert info["interval"] == 1  # prob 10/10 stops after the first primitive step
+
+
+def test_graph_api_matches_oracle_stream():
+    """Graph.step on the device == oracle in Philox mode with the graph's (seed, epoch) stream."""
+    from gym_PBN.envs.bittner import utils
+
+    g = utils.spawn(total_genes=28, seed=123)
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    assert g.getIDs() == ids and g.N == 28
+    st0 = [(i * 7) % 2 for i in range(28)]
+    g.setState(st0)
+    assert tuple(g.getState()) == tuple(st0) and g.getState()[ids[3]] == st0[3] and g.nodes[5].value == st0[5]
+    g.flipNode(4)
+    ost = np.array([st0], np.uint8)
+    ost[0, 4] ^= 1
+    s = g.step()
+    orc.rollout(onet, ost, 1, orc.Draws(seed=123, epoch=g.sim.epoch - 1))
+    assert tuple(s) == tuple(ost[0])
+    g.step(steps=500)
+    orc.rollout(onet, ost, 500, orc.Draws(seed=123, epoch=g.sim.epoch - 1))
+    assert tuple(g.getState()) == tuple(ost[0])
+    g.synch_step()
+    orc.rollout(onet, ost, 1, orc.Draws(seed=123, epoch=g.sim.epoch - 1), sync=True)
+    assert tuple(g.getState()) == tuple(ost[0])
+    with pytest.raises(ValueError):
+        g.flipNode(28)
+
+
+def test_bittner28_env_with_fixture_attractors():
+    import gym_PBN
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=64, seed=5)
+    core = env.unwrapped
+    (state, target), info = env.reset(seed=5)
+    assert len(state) == 28 and core.is_attracting_state(state) and core.target in atts
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    oenv = orc.Env(orc.ENV_TARGET, 28, attractors=atts, horizon=100, max_inner=64)
+    ost = np.array([state], np.uint8)
+    ons, ota = np.zeros(1, np.int32), np.array([atts.index(core.target)], np.int32)
+    for t in range(40):
+        a = (t * 5) % 29
+        epoch = core.sim.epoch
+        obs, r, term, trunc, info = env.step(a)
+        oobs, orew, oterm, otrunc, oin = orc.env_step(onet, oenv, ost, ons, ota, np.array([[a]], np.int32),
+                                                      orc.Draws(seed=5, epoch=epoch))
+        assert np.array_equal(obs, oobs[0]) and (r, term) == (int(orew[0]), bool(oterm[0]))
+        assert info["inner_steps"] == int(oin[0]) and core.n_steps == int(ons[0])
+        assert core.getTargetIdx() == int("".join(str(int(obs[ids.index(g)])) for g in core.target_nodes), 2)
+        assert r == (20 if core.in_target(obs) else -5)
+        if term or trunc:
+            break
+
+
+def test_make_bittner_100_and_200_default_attractors():
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/Bittner-100-v0", seed=1)
+    core = env.unwrapped
+    assert core.graph.N == 100 and len(core.all_attractors) == 4 and core.horizon == 69
+    (state, target), info = env.reset(seed=1)
+    for _ in range(5):
+        obs, r, term, trunc, info = env.step(0)
+        assert obs.shape == (100,) and r in (20, -5)
+    env = gym_PBN.make("gym-PBN/Bittner-200-v0", seed=1)  # example.py:53; the shipped 200-gene set has 199 nodes
+    assert env.unwrapped.graph.N == 199
+    env.reset(seed=2)
+    env.step(0)
+    with pytest.raises(FileNotFoundError):
+        gym_PBN.make("gym-PBN/Bittner-7-v0")
+
+
+def test_multi_env_list_and_tensor_actions():
+    import gym_PBN
+
+    z = load("b28_multi_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/BittnerMulti-28-v0", all_attractors=atts, max_inner_steps=64, seed=9)
+    core = env.unwrapped
+    (state, target), info = env.reset(seed=9)
+    assert core.target is atts[-1] or core.target == atts[-1]
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    oenv = orc.Env(orc.ENV_MULTI, 28, attractors=atts, horizon=100, max_inner=64, dedup=0)
+    ost = np.array([state], np.uint8)
+    ons, ota = np.zeros(1, np.int32), np.array([len(atts) - 1], np.int32)
+    for t in range(30):
+        acts = [(3 * t) % 29, (7 * t + 1) % 29, (3 * t) % 29 if t % 2 else 0]
+        epoch = core.sim.epoch
+        if t % 3 == 0:
+            obs, r, term, trunc, info = env.step(torch.tensor(acts))
+            eff = sorted(set(acts))
+        else:
+            obs, r, term, trunc, info = env.step(list(acts))
+            eff = acts
+        oobs, orew, oterm, otrunc, oin = orc.env_step(onet, oenv, ost, ons, ota, np.array([eff], np.int32),
+                                                      orc.Draws(seed=9, epoch=epoch))
+        assert tuple(obs) == tuple(oobs[0]) and (r, term, trunc) == (int(orew[0]), bool(oterm[0]), bool(otrunc[0]))
+        if term or trunc:
+            break
+
+
+def test_vector_env_matches_oracle():
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=32)
+    B, seed = 4096, 17
+    vec = PBNVectorEnv(env, B, seed=seed)
+    obs, info = vec.reset()
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    oenv = orc.Env(orc.ENV_TARGET, 28, attractors=atts, horizon=100, max_inner=32)
+    ost = np.zeros((B, 28), np.uint8)
+    ons, ota = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    assert np.array_equal(obs.cpu().numpy(), ost)
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(25):
+        act = rng.integers(0, 29, size=(B, 1)).astype(np.int32)
+        obs, rew, term, trunc, info = vec.step(torch.from_numpy(act))
+        oobs, orew, oterm, otrunc, oin = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + 2 * t))
+        assert np.array_equal(rew.cpu().numpy(), orew) and np.array_equal(term.cpu().numpy(), oterm.astype(bool))
+        assert np.array_equal(vec.sim.unpack(info["final_obs_packed"]).cpu().numpy(), oobs)
+        done = (oterm | otrunc).astype(np.uint8)
+        episodes += int(done.sum())
+        orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=2 + 2 * t), mask=done)
+        assert np.array_equal(obs.cpu().numpy(), ost)  # auto-reset envs observe their new state
+    red = vec.stats.reduced()
+    assert red["episodes"] == episodes and red["env_steps"] == 25 * B and episodes > 0
+    sd = vec.state_dict()
+    vec2 = PBNVectorEnv(env, B, seed=0)
+    vec2.load_state_dict(sd)
+    act = rng.integers(0, 29, size=(B, 1)).astype(np.int32)
+    o1 = vec.step(torch.from_numpy(act))[0].clone()
+    o2 = vec2.step(torch.from_numpy(act))[0]
+    assert torch.equal(o1, o2)
+
+
+def test_vector_env_pbn_family_and_host_step():
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    env = gym_PBN.make("gym-PBN/PBN-v0", logic_func_data=EX5, goal_config=dict(GOAL))
+    vec = PBNVectorEnv(env, 1000, seed=4)
+    obs, _ = vec.reset()
+    assert obs.shape == (1000, 5) and int(obs[:, 0].sum()) == 0
+    o, r, te, tr = vec.step_host(np.random.default_rng(1).integers(0, 5, size=(1000, 1)))
+    assert o.shape == (1000, 5) and set(np.unique(r)) <= {20, -4, -5} and not tr.any()
+
+
+def test_compute_ssd_hist_drop_in():
+    import gym_PBN
+    from gym_PBN.utils.eval import compute_ssd_hist, total_variation
+
+    env = gym_PBN.make("gym-PBN/Bittner-100-v0", all_attractors=[[("*",) * 100], [("*",) * 100]], seed=3)
+    df, fig = compute_ssd_hist(env.unwrapped, iters=1_200_000, resets=300, bit_flip_prob=0.01, seed=3)
+    vals = np.asarray(df["Value"])
+    assert vals.shape == (128,) and abs(vals.sum() - 1.0) < 1e-9 and list(df.index[:2]) == ["0000000", "0000001"]
+    z = load("b100_ssd_long.npz")
+    floor = total_variation(z["ssd"][0], z["ssd"][1])
+    assert total_variation(vals, z["ssd"][0]) <= 3 * floor
