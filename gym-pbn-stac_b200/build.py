@@ -16,11 +16,13 @@ NVCC_FLAGS = [
 ]
 
 
-def build(force=False, verbose=False):
-    if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
-        return LIB
+def build(force=False, verbose=False, extra=(), out=None):
+    """extra/out: experiment builds (e.g. extra=["-DPBN_SSD_MIN_BLOCKS=6"], out=lib/variant.so)."""
+    target = Path(out) if out else LIB
+    if not force and target.exists() and all(target.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
+        return target
     LIB.parent.mkdir(exist_ok=True)
-    cmd = ["nvcc", *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{HERE / 'csrc'}", "-o", str(LIB), *map(str, SRC)]
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, f"-I{ROOT / 'include'}", f"-I{HERE / 'csrc'}", "-o", str(target), *map(str, SRC)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     (HERE / "lib" / "ptxas.log").write_text(res.stderr)
     if res.returncode != 0:
@@ -28,7 +30,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libpbn_b200.so")
     if verbose:
         print(res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

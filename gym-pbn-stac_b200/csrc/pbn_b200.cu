@@ -450,8 +450,11 @@ __device__ __forceinline__ int ssd_bucket(const SsdParams &sp, const u32 *s_tgt,
     return b;
 }
 
+#ifndef PBN_SSD_MIN_BLOCKS
+#define PBN_SSD_MIN_BLOCKS 4
+#endif
 template <int NET, int MODE, int TQ, bool HAS_ENV>
-__global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, DrawView dv, SsdParams sp, u32 *state,
+__global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView nv, EnvView ev, DrawView dv, SsdParams sp, u32 *state,
                                                    long long chains, long long env0, int iters,
                                                    unsigned long long *hist) {
     unsigned char *blob = smem_raw;
@@ -475,48 +478,86 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_ssd(NetView nv, EnvView ev, DrawV
     const int w32 = nv.w32;
     const u32 n = (u32)nv.n;
     Col st{sst + threadIdx.x};
-    if (e < chains) load_state(st, state, chains, e, w32);
+    const bool active = e < chains;
+    if (active) load_state(st, state, chains, e, w32);
     __syncthreads();
-    if (e < chains) {
+    // a warp runs as long as its first chain exists; its missing lanes (tail of the job) still take part in the
+    // warp-cooperative perturbation stream but own no state
+    if (e - (threadIdx.x & 31) < chains) {
         Draw<MODE> d;
         d.init(dv, e, env0 + e);
         const float inv = sp.inv;
         const bool flips = inv <= 0.f;
-        u32 pos = 0;
-        if constexpr (MODE == PBN_DRAW_PHILOX) pos = flips ? geom_gap(d.next(), inv) : 0xFFFFFFFFu;
-        int cur = ssd_bucket(sp, s_tgt, st);
+        // PHILOX perturbation: ONE Bernoulli(p) renewal process per group of 32 consecutive chains over the interleaved
+        // index c = node*32 + lane (window = 32*n positions per iteration).  Each round every lane draws one geometric
+        // gap from its own stream, a warp prefix sum turns the 32 gaps into 32 event positions, and an event inside the
+        // current window flips bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n independent
+        // Bernoulli(p) per chain per iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
+        const u32 lane = threadIdx.x & 31u;
+        const u32 W = n * 32u;
+        u32 evp = 0xFFFFFFFFu;  // this lane's pending event, relative to the window start (none)
+        u32 last_p1 = 0;        // (position of the last generated event) + 1, relative to the window start
+        u32 *warp_cols = sst + (threadIdx.x & ~31u);
+        const long long warp_left = chains - (e - lane);
+        const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
+        int cur = active ? ssd_bucket(sp, s_tgt, st) : 0;
         u32 run = 0;
         for (int t = 0; t < iters; t++) {
-            const int b = ssd_bucket(sp, s_tgt, st);
-            if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
-                if (sp.smem_hist) atomicAdd(&shist[cur], run);
-                else atomicAdd(&hist[cur], (unsigned long long)run);
-                cur = b; run = 0;
+            if (active) {
+                const int b = ssd_bucket(sp, s_tgt, st);
+                if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
+                    if (sp.smem_hist) atomicAdd(&shist[cur], run);
+                    else atomicAdd(&hist[cur], (unsigned long long)run);
+                    cur = b; run = 0;
+                }
+                run++;
             }
-            run++;
             if constexpr (MODE == PBN_DRAW_REPLAY) {
-                for (u32 j = 0; j < n; j++)
-                    if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
+                if (active)
+                    for (u32 j = 0; j < n; j++)
+                        if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
             } else {
                 if (flips) {
-                    while (pos < n) { st.flip(pos); pos += 1u + geom_gap(d.next(), inv); }
-                    pos -= n;
+                    for (;;) {
+                        if (evp < W) {
+                            const u32 tl = evp & 31u, bit = evp >> 5;
+                            if (tl < nvalid) atomicXor(warp_cols + tl + (bit >> 5) * PBN_BLOCK, 1u << (bit & 31u));
+                            evp = 0xFFFFFFFFu;
+                        }
+                        if (last_p1 > W) break;  // the last generated event lies beyond this window
+                        u32 pre = 1u + geom_gap(d.next(), inv);
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const u32 o = __shfl_up_sync(0xFFFFFFFFu, pre, off);
+                            if (lane >= (u32)off) pre += o;
+                        }
+                        evp = last_p1 - 1u + pre;
+                        last_p1 = __shfl_sync(0xFFFFFFFFu, evp, 31) + 1u;
+                    }
+                    if (evp != 0xFFFFFFFFu) evp -= W;
+                    last_p1 -= W;
+                    __syncwarp();
                 }
             }
-            micro_step<NET, MODE, TQ>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
-            if constexpr (HAS_ENV) {
-                if (!ev.force) {
-                    int in = 1;
-                    while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE, TQ>(nv, blob, st, d); in++; }
+            if (active) {
+                micro_step<NET, MODE, TQ>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
+                if constexpr (HAS_ENV) {
+                    if (!ev.force) {
+                        int in = 1;
+                        while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE, TQ>(nv, blob, st, d); in++; }
+                    }
                 }
             }
+            if constexpr (MODE == PBN_DRAW_PHILOX) __syncwarp();  // updates land before the next iteration's cross-lane flips
         }
-        if (run) {
-            if (sp.smem_hist) atomicAdd(&shist[cur], run);
-            else atomicAdd(&hist[cur], (unsigned long long)run);
+        if (active) {
+            if (run) {
+                if (sp.smem_hist) atomicAdd(&shist[cur], run);
+                else atomicAdd(&hist[cur], (unsigned long long)run);
+            }
+            store_state(st, state, chains, e, w32);
+            d.done(dv, e);
         }
-        store_state(st, state, chains, e, w32);
-        d.done(dv, e);
     }
     if (sp.smem_hist) {
         __syncthreads();
@@ -710,6 +751,9 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     if (env && env->net != net) return fail(PBN_ERR_ARG, "env belongs to another network");
     if (int rc = check_draws(draws)) return rc;
     if (chains == 0 || iters == 0) return PBN_OK;
+    if (draws->mode == PBN_DRAW_PHILOX && p > 0 && (env0 & 31))
+        return fail(PBN_ERR_ARG, "env0 must be a multiple of 32: the perturbation stream is shared by groups of 32 consecutive chain ids");
+    if (p > 0 && p < 1e-7) return fail(PBN_ERR_UNSUPPORTED, "bit_flip_prob below 1e-7 is not supported (gap law is truncated at 2^26)");
     const NetView &nv = net->v;
     const DrawView dv = make_draws(draws);
     SsdParams sp;

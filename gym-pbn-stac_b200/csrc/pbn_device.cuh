@@ -149,8 +149,8 @@ __device__ __forceinline__ float log2f_poly(float x) {
 __device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
     float u = __fmul_rn(__fadd_rn((float)(r >> 9), 0.5f), 1.0f / 8388608.0f);
     float g = __fmul_rn(log2f_poly(u), inv);
-    if (!(g < 1.0e9f)) return 1000000000u;
-    return (u32)g;  // g >= 0: truncation
+    if (!(g < 67108864.0f)) return 67108864u;  // gaps are capped at 2^26 so a warp prefix sum of 32 gaps fits 32 bits
+    return (u32)g;                              // g >= 0: truncation
 }
 
 // ----------------------------------------------------------------------------------------------- state column

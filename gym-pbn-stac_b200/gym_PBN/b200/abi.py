@@ -4,10 +4,11 @@ The CUDA library is the only compute path: if libpbn_b200.so is missing or fails
 raises — there is no CPU fallback anywhere in the product.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parents[2]  # gym-pbn-stac_b200/
-LIB_PATH = PKG_ROOT / "lib" / "libpbn_b200.so"
+LIB_PATH = Path(os.environ.get("PBN_B200_LIB", PKG_ROOT / "lib" / "libpbn_b200.so"))  # override = kernel experiments only
 
 NET_TT, NET_PRED = 0, 1
 ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD = range(6)

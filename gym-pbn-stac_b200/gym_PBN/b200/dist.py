@@ -14,13 +14,16 @@ def world():
     return 0, 1
 
 
-def shard_range(total: int, rank: int = None, world_size: int = None):
-    """Contiguous [start, stop) of global env ids owned by `rank` (first ranks take the remainder)."""
+def shard_range(total: int, rank: int = None, world_size: int = None, align: int = 1):
+    """Contiguous [start, stop) of global env ids owned by `rank` (first ranks take the remainder).  With align > 1
+    every boundary is a multiple of `align` (the SSD perturbation stream is shared by groups of 32 consecutive ids)."""
     if rank is None or world_size is None:
         rank, world_size = world()
-    base, rem = divmod(int(total), int(world_size))
+    units = -(-int(total) // align)
+    base, rem = divmod(units, int(world_size))
     start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
+    stop = start + base + (1 if rank < rem else 0)
+    return min(start * align, int(total)), min(stop * align, int(total))
 
 
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:

@@ -48,7 +48,7 @@ def ssd_histogram(env, iters, chains, bit_flip_prob=0.01, seed=None, distributed
     """Device-side estimate for one of our envs: chains start from env.reset() states (or uniform random states when the
     env has no attractor list), sharded over ranks by global chain id.  Returns (int64 device histogram, total iterations)."""
     net = env.network
-    start, stop = pdist.shard_range(chains) if distributed else (0, chains)
+    start, stop = pdist.shard_range(chains, align=32) if distributed else (0, chains)
     local = stop - start
     seed = env._next_seed() if seed is None else seed
     sim = engine.Simulator(net, max(local, 1), seed=seed, env0=start)

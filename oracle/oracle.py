@@ -224,9 +224,11 @@ def rand_state(net, B, draws, env0=0):
 def ssd(net, env, state, iters, p, tgt_nodes, draws, env0=0):
     tgt = np.ascontiguousarray(tgt_nodes, np.int32)
     hist = np.zeros(1 << len(tgt), np.uint64)
-    lib().orc_ssd(C.byref(net.c), C.byref(env.c) if env is not None else None, _p(state), C.c_int64(state.shape[0]),
-                  C.c_int64(env0), C.c_int64(iters), C.c_double(p), _p(tgt), C.c_int(len(tgt)), _p(hist),
-                  C.byref(draws.c))
+    rc = lib().orc_ssd(C.byref(net.c), C.byref(env.c) if env is not None else None, _p(state), C.c_int64(state.shape[0]),
+                       C.c_int64(env0), C.c_int64(iters), C.c_double(p), _p(tgt), C.c_int(len(tgt)), _p(hist),
+                       C.byref(draws.c))
+    if rc:
+        raise ValueError("orc_ssd: env0 must be a multiple of 32 in Philox mode (groups of 32 chains share the flip stream)")
     return hist
 
 

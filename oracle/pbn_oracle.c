@@ -166,7 +166,7 @@ static inline float orc_log2f_poly(float x) { /* x > 0, normal */
 uint32_t orc_geom(uint32_t r, float inv) {
     float u = ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
     float g = orc_log2f_poly(u) * inv;
-    if (!(g < 1.0e9f)) return 1000000000u;
+    if (!(g < 67108864.0f)) return 67108864u; /* capped at 2^26: 32 summed gaps fit 32 bits */
     return (uint32_t)g;
 }
 float orc_geom_inv(double p) { /* host helper shared by tests: 1/log2(1-p) as float */
@@ -402,47 +402,75 @@ int orc_rand_state(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, c
 /* K3: utils/eval.py:76-103 _ssd_run for `chains` chains x `iters` iterations, model=None.
    Per iteration: hist[bucket(state)] += 1 (before stepping, :88-89); flip each node w.p. p (:92-95);
    env.step(0) (:96) = PBNTargetEnv.step: one update, then until attracting (cap max_inner).
-   REPLAY: n doubles per iteration then the step's draws.  PHILOX: flips are a geometric-skip Bernoulli
-   process over the linear index (iteration*n + node) — the same law as n independent Bernoulli(p) per
-   iteration, using 1+#flips draws instead of n.
+   REPLAY: n doubles per chain per iteration, then the step's draws.
+   PHILOX: the flips of each GROUP of 32 consecutive chain ids (global id >> 5) are one Bernoulli(p) renewal
+   process over the interleaved index c = node*32 + lane, window = 32*n positions per iteration: in every round each
+   of the 32 lanes draws one geometric gap from its own stream, event k of the round sits at
+   (last event) + sum of (1+gap) over lanes 0..k, and an event inside the window flips node c>>5 of chain c&31.
+   That is the same law as n independent Bernoulli(p) draws per chain per iteration, at ~1 draw per chain.
    bucket = target-node bits MSB-first (pbn_target.py:383-391).  hist is uint64 [2^g], summed over chains. */
 int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains, int64_t env0, int64_t iters,
             double p, const int32_t *tgt_nodes, int g, uint64_t *hist, const OrcDraws *dr) {
     const int n = net->n;
     const int64_t nb = (int64_t)1 << g;
     const float inv = orc_geom_inv(p);
+    const int flips = !(inv > 0);
+    const uint32_t W = (uint32_t)n * 32u, NONE = 0xFFFFFFFFu;
+    if (dr->mode == ORC_PHILOX && flips && (env0 & 31)) return 1;
     int nthreads = 1;
 #ifdef _OPENMP
     extern int omp_get_max_threads(void); extern int omp_get_thread_num(void);
     nthreads = omp_get_max_threads();
 #endif
     uint64_t *priv = (uint64_t *)calloc((size_t)(nthreads * nb), sizeof(uint64_t));
+    const int64_t groups = (chains + 31) / 32;
 #pragma omp parallel for schedule(static) if (chains >= 256)
-    for (int64_t e = 0; e < chains; e++) {
+    for (int64_t gi = 0; gi < groups; gi++) {
         int tid = 0;
 #ifdef _OPENMP
         tid = omp_get_thread_num();
 #endif
         uint64_t *h = priv + (int64_t)tid * nb;
-        Dr d; dr_init(&d, dr, e, env0 + e);
-        uint8_t *st = state + e * n;
-        int64_t pos = 0;
-        if (d.mode == ORC_PHILOX) pos = inv > 0 ? INT64_MAX / 2 : (int64_t)orc_geom(dr_u32(&d), inv);
+        const int64_t gb = gi * 32;
+        Dr d[32];
+        uint32_t ev[32], last_p1 = 0;
+        for (int l = 0; l < 32; l++) { dr_init(&d[l], dr, gb + l < chains ? gb + l : 0, env0 + gb + l); ev[l] = NONE; }
         for (int64_t t = 0; t < iters; t++) {
-            int64_t b = 0;
-            for (int k = 0; k < g; k++) b = (b << 1) | st[tgt_nodes[k]];
-            h[b]++;
-            if (d.mode == ORC_REPLAY) {
-                for (int j = 0; j < n; j++) if (dr_dbl(&d) < p) st[j] ^= 1; /* graph.flipNode(j), eval.py:92-95 */
-            } else {
-                while (pos < n) { st[pos] ^= 1; pos += 1 + (int64_t)orc_geom(dr_u32(&d), inv); }
-                pos -= n;
+            for (int l = 0; l < 32 && gb + l < chains; l++) {
+                const uint8_t *st = state + (gb + l) * n;
+                int64_t b = 0;
+                for (int k = 0; k < g; k++) b = (b << 1) | st[tgt_nodes[k]];
+                h[b]++;
             }
-            micro_step(net, st, &d);
-            int in = 1;
-            while (env && !env->force && !is_attracting(env, st, n) && in < env->max_inner) { micro_step(net, st, &d); in++; }
+            if (dr->mode == ORC_REPLAY) {
+                for (int l = 0; l < 32 && gb + l < chains; l++) {
+                    uint8_t *st = state + (gb + l) * n;
+                    for (int j = 0; j < n; j++) if (dr_dbl(&d[l]) < p) st[j] ^= 1; /* graph.flipNode(j), eval.py:92-95 */
+                }
+            } else if (flips) {
+                for (;;) {
+                    for (int l = 0; l < 32; l++)
+                        if (ev[l] < W) {
+                            uint32_t tl = ev[l] & 31u, bit = ev[l] >> 5;
+                            if (gb + tl < chains) state[(gb + tl) * n + bit] ^= 1;
+                            ev[l] = NONE;
+                        }
+                    if (last_p1 > W) break;
+                    uint32_t pre = 0;
+                    for (int l = 0; l < 32; l++) { pre += 1u + orc_geom(dr_u32(&d[l]), inv); ev[l] = last_p1 - 1u + pre; }
+                    last_p1 = ev[31] + 1u;
+                }
+                for (int l = 0; l < 32; l++) if (ev[l] != NONE) ev[l] -= W;
+                last_p1 -= W;
+            }
+            for (int l = 0; l < 32 && gb + l < chains; l++) {
+                uint8_t *st = state + (gb + l) * n;
+                micro_step(net, st, &d[l]);
+                int in = 1;
+                while (env && !env->force && !is_attracting(env, st, n) && in < env->max_inner) { micro_step(net, st, &d[l]); in++; }
+            }
         }
-        dr_done(&d, dr, e);
+        for (int l = 0; l < 32 && gb + l < chains; l++) dr_done(&d[l], dr, gb + l);
     }
     for (int t = 0; t < nthreads; t++) for (int64_t b = 0; b < nb; b++) hist[b] += priv[t * nb + b];
     free(priv);

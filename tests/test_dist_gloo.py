@@ -24,7 +24,8 @@ def _worker(rank, world, port, out_dir):
     sets, ids = orc.load_bittner("28_15_median")
     net = orc.net_from_predictor_sets(sets, ids)
     total, iters, seed = 600, 50, 11
-    start, stop = pdist.shard_range(total)
+    start, stop = pdist.shard_range(total, align=32)
+    assert start % 32 == 0
     st = orc.rand_state(net, stop - start, orc.Draws(seed=seed, epoch=0), env0=start)
     h = orc.ssd(net, None, st, iters, 0.01, np.arange(5, dtype=np.int32), orc.Draws(seed=seed, epoch=1), env0=start)
     t = torch.from_numpy(h.astype(np.int64))

@@ -150,6 +150,8 @@ def test_shard_range_covers_everything():
         assert spans[0][0] == 0 and spans[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    spans = [shard_range(1000, r, 3, align=32) for r in range(3)]
+    assert spans == [(0, 352), (352, 704), (704, 1000)]
 
 
 def test_product_never_imports_the_oracle():
