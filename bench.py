@@ -79,6 +79,8 @@ class ClockSampler:
 def cpu_sample(target_seconds=12.0):
     """Times the oracle port (oracle/pbn_oracle.c, OpenMP over chains) on a bounded sample of the same workload."""
     sys.path.insert(0, str(ROOT / "oracle"))
+    # all host threads (torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every core)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("PBN_BENCH_THREADS", str(os.cpu_count() or 1))
     import oracle as orc
 
     sets, ids = orc.load_bittner(NET_NAME)
@@ -256,7 +258,7 @@ def run_gpu(args):
                     "frac": hbm_alg / t_kernel / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
-        cpu = cpu_sample(12.0)
+        cpu = cpu_sample(12.0) if world == 1 else None  # reported on rank 0 at N=1 only
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": t_steps * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": workload_config(n_gpus), "clocks": clocks,
