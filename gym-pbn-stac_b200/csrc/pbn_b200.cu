@@ -79,15 +79,17 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         }
         const int ts = ((fmax - 1 + 3) / 4) * 4 > 0 ? ((fmax - 1 + 3) / 4) * 4 : 4;
         v.fmax = fmax; v.ts = ts;
+        v.tsq_stride = (ts / 4) | 1;  // odd number of quads per row (bank-conflict padding)
+        const int row = v.tsq_stride * 4;
         v.off_thr = 0;
-        v.off_rec = n * ts * 4;
+        v.off_rec = n * row * 4;
         blob.resize((size_t)v.off_rec + (size_t)n * fmax * 8);
         u32 *thr = reinterpret_cast<u32 *>(blob.data());
         uint2 *rec = reinterpret_cast<uint2 *>(blob.data() + v.off_rec);
         for (int i = 0; i < n; i++) {
             const int q0 = d->pr_off[i], f = d->pr_off[i + 1] - q0;
-            for (int k = 0; k < ts; k++)
-                thr[i * ts + k] = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
+            for (int k = 0; k < row; k++)
+                thr[i * row + k] = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
             for (int k = 0; k < fmax; k++) {
                 const int q = q0 + (k < f ? k : f - 1);
                 u32 packed = 0;
@@ -294,48 +296,6 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
         micro_step<NET, MODE>(nv, blob, st, d); in = 1;
         rew = pbcn_reward(ev, att_off, cubes, st, w32, tm);
     } break;
-    case PBN_ENV_TARGET: {  // pbn_target.py:261-280, reward :303-326
-        int a = act[0];
-        int ns = n_steps[e] + 1;
-        n_steps[e] = ns;
-        if (a != 0) st.flip(a - 1);
-        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
-        while (!ev.force && in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) {
-            micro_step<NET, MODE>(nv, blob, st, d); in++;
-        }
-        int ta = target_att[e];
-        if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
-        tr = (ns == ev.horizon);
-    } break;
-    case PBN_ENV_MULTI: {  // pbn_target_multi.py:119-154, reward :201-225
-        int cnt = 0;
-        int ns = n_steps[e] + 1;
-        n_steps[e] = ns;
-        for (int k = 0; k < K; k++) {
-            int a = act[k];
-            if (a < 0) continue;
-            if (ev.dedup) {
-                bool dup = false;
-                for (int j = 0; j < k; j++) dup |= (act[j] == a);
-                if (dup) continue;
-            }
-            cnt++;
-            if (a != 0) st.flip(a - 1);
-        }
-        for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
-        obs_is_state = false;
-        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
-        while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, ob, w32)) {
-            micro_step<NET, MODE>(nv, blob, st, d);
-            for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
-            in++;
-        }
-        int ta = target_att[e];
-        // in_target returns at the first mismatch of the FIRST cube (Q12)
-        if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew = 1000; tm = 1; }
-        rew -= cnt;
-        tr = (ns == ev.horizon);
-    } break;
     case PBN_ENV_PBN_SD: {  // sampled_data.py:52-88
         int a = act[0], interval = act[1];
         for (int i = 0; i < interval; i++) {
@@ -366,6 +326,97 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     truncated[e] = (unsigned char)tr;
     if (inner_steps) inner_steps[e] = in;
     d.done(dv, e);
+}
+
+// K2 for the two step-until-attractor envs (PBNTargetEnv, PBNTargetMultiEnv).  The inner loop is unbounded in the
+// reference and heavy-tailed in practice (1 .. 40 000 updates per env.step): with one env per thread a
+// warp, and then its whole block, lives as long as its slowest env.  So the kernel is PERSISTENT: each block owns a
+// contiguous range of envs and its threads pull the next env from a block-local counter the moment they finish one, in a
+// flat loop whose every trip is "one attractor test + at most one update" for every lane — lanes never wait at the end
+// of an inner loop.  An env's result does not depend on which thread ran it (its Philox stream is keyed by its id).
+template <int NET, int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+                                                            const int *target_att, const int *actions, int K, u32 *obs_state,
+                                                            int *reward, unsigned char *terminated, unsigned char *truncated,
+                                                            int *inner_steps, long long B, long long env0, long long per_block) {
+    unsigned char *blob = smem_raw;
+    unsigned char *img = smem_raw + nv.blob_bytes;
+    u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    const int w32 = nv.w32;
+    __shared__ int s_next;
+    stage(blob, nv.blob, nv.blob_bytes);
+    stage(img, ev.img, ev.img_bytes);
+    const int *att_off = reinterpret_cast<const int *>(img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
+    const long long lo = (long long)blockIdx.x * per_block;
+    const long long hi = lo + per_block < B ? lo + per_block : B;
+    if (threadIdx.x == 0) s_next = PBN_BLOCK;  // the first PBN_BLOCK envs of the range are taken statically
+    __syncthreads();
+    const bool multi = ev.kind == PBN_ENV_MULTI;
+    Col st{sst + threadIdx.x}, ob{sst + w32 * PBN_BLOCK + threadIdx.x};
+    Draw<MODE> d;
+    bool have = false;
+    long long e = 0, nxt = lo + threadIdx.x;
+    int in = 0, pend = 0;
+    for (;;) {
+        if (!have) {
+            if (nxt >= hi) break;
+            e = nxt;
+            load_state(st, state, B, e, w32);
+            d.init(dv, e, env0 + e);
+            const int *act = actions + e * K;
+            n_steps[e] += 1;
+            if (!multi) {  // pbn_target.py:261-269
+                const int a = act[0];
+                if (a != 0) st.flip(a - 1);
+            } else {  // pbn_target_multi.py:120-134
+                int cnt = 0;
+                for (int k = 0; k < K; k++) {
+                    const int a = act[k];
+                    if (a < 0) continue;
+                    if (ev.dedup) {
+                        bool dup = false;
+                        for (int j = 0; j < k; j++) dup |= (act[j] == a);
+                        if (dup) continue;
+                    }
+                    cnt++;
+                    if (a != 0) st.flip(a - 1);
+                }
+                pend = -cnt;  // reward -= len(actions)
+                for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
+            }
+            micro_step<NET, MODE>(nv, blob, st, d);
+            in = 1;
+            have = true;
+        }
+        // while not force and not is_attracting_state(state): graph.step()                  (pbn_target.py:270-271)
+        // while not is_attracting_state(observation): observation = graph.step()            (pbn_target_multi.py:135-146)
+        const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting(ev, att_off, cubes, multi ? ob : st, w32);
+        if (!done) {
+            micro_step<NET, MODE>(nv, blob, st, d);
+            if (multi)
+                for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
+            in++;
+        } else {
+            int rew, tm = 0;
+            const int ta = target_att[e];
+            if (!multi) {  // PBNTargetEnv._get_reward, pbn_target.py:303-326: any cube of the target attractor
+                if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
+            } else {  // in_target returns at the first mismatch of the FIRST cube (Q12), pbn_target_multi.py:190-225
+                rew = pend;
+                if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew += 1000; tm = 1; }
+            }
+            store_state(st, state, B, e, w32);
+            if (obs_state) store_state(multi ? ob : st, obs_state, B, e, w32);
+            reward[e] = rew;
+            terminated[e] = (unsigned char)tm;
+            truncated[e] = (unsigned char)(n_steps[e] == ev.horizon);
+            if (inner_steps) inner_steps[e] = in;
+            d.done(dv, e);
+            have = false;
+            nxt = lo + atomicAdd(&s_next, 1);
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------- reset
@@ -450,6 +501,105 @@ __device__ __forceinline__ int ssd_bucket(const SsdParams &sp, const u32 *s_tgt,
     return b;
 }
 
+struct SsdLoopArgs {
+    const NetView &nv;
+    const EnvView &ev;
+    const SsdParams &sp;
+    const unsigned char *blob;
+    const int *att_off;
+    const u32 *cubes;
+    const u32 *s_tgt;
+    u32 *shist;
+    unsigned long long *hist;
+    u32 *sst;
+    int iters;
+    u32 nvalid;
+};
+
+// inclusive warp prefix sum; shfl.up's predicate output says whether the source lane exists, so each step is two
+// instructions (SHFL + predicated add)
+__device__ __forceinline__ u32 warp_scan_add(u32 v) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+        asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }"
+                     : "+r"(v) : "r"(off));
+    return v;
+}
+
+// The SSD iteration loop of one warp.  FULL = every lane owns a chain (all warps but possibly the last of the job).
+// PHILOX perturbation: ONE Bernoulli(p) renewal process per group of 32 consecutive chains over the interleaved index
+// c = node*32 + lane (window = 32*n positions per iteration).  Each round every lane draws one geometric gap from its
+// own stream, a warp prefix sum turns the 32 gaps into 32 event positions, and an event inside the current window flips
+// bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n independent Bernoulli(p) per chain per
+// iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
+template <int NET, int MODE, int TQ, bool HAS_ENV, bool FULL>
+__device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Draw<MODE> &d) {
+    const NetView &nv = a.nv;
+    const SsdParams &sp = a.sp;
+    const u32 lane = threadIdx.x & 31u;
+    const bool active = FULL || lane < a.nvalid;
+    const u32 n = (u32)nv.n, W = n * 32u;
+    const float inv = sp.inv;
+    const bool flips = inv <= 0.f;
+    u32 evp = 0xFFFFFFFFu;  // this lane's pending event, relative to the window start (none)
+    u32 last_p1 = 0;        // (position of the last generated event) + 1, relative to the window start
+    char *warp_cols = reinterpret_cast<char *>(a.sst + (threadIdx.x & ~31u));
+    int cur = active ? ssd_bucket(sp, a.s_tgt, st) : 0;
+    u32 run = 0;
+    for (int t = 0; t < a.iters; t++) {
+        if (active) {
+            const int b = ssd_bucket(sp, a.s_tgt, st);
+            if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
+                if (sp.smem_hist) atomicAdd(&a.shist[cur], run);
+                else atomicAdd(&a.hist[cur], (unsigned long long)run);
+                cur = b; run = 0;
+            }
+            run++;
+        }
+        if constexpr (MODE == PBN_DRAW_REPLAY) {
+            if (active)
+                for (u32 j = 0; j < n; j++)
+                    if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
+        } else {
+            if (flips) {
+                for (;;) {
+                    if (evp < W) {
+                        const u32 tl = evp & 31u;
+                        // word (node>>5) of column tl: byte offset = tl*4 + (node>>5)*1024, node = evp>>5
+                        if (FULL || tl < a.nvalid)
+                            atomicXor(reinterpret_cast<u32 *>(warp_cols + tl * 4u + ((evp >> 10) << 10)), 1u << ((evp >> 5) & 31u));
+                        evp = 0xFFFFFFFFu;
+                    }
+                    if (last_p1 > W) break;  // the last generated event lies beyond this window
+                    const u32 pre = warp_scan_add(1u + geom_gap(d.next(), inv));
+                    evp = last_p1 - 1u + pre;
+                    last_p1 = __shfl_sync(0xFFFFFFFFu, evp, 31) + 1u;
+                }
+                if (evp != 0xFFFFFFFFu) evp -= W;
+                last_p1 -= W;
+                __syncwarp();
+            }
+        }
+        if (active) {
+            micro_step<NET, MODE, TQ>(nv, a.blob, st, d);  // env.step(0): pbn_target.py:269-271
+            if constexpr (HAS_ENV) {
+                if (!a.ev.force) {
+                    int in = 1;
+                    while (in < a.ev.max_inner && !is_attracting(a.ev, a.att_off, a.cubes, st, nv.w32)) {
+                        micro_step<NET, MODE, TQ>(nv, a.blob, st, d);
+                        in++;
+                    }
+                }
+            }
+        }
+        if constexpr (MODE == PBN_DRAW_PHILOX) __syncwarp();  // updates land before the next iteration's cross-lane flips
+    }
+    if (active && run) {
+        if (sp.smem_hist) atomicAdd(&a.shist[cur], run);
+        else atomicAdd(&a.hist[cur], (unsigned long long)run);
+    }
+}
+
 #ifndef PBN_SSD_MIN_BLOCKS
 #define PBN_SSD_MIN_BLOCKS 4
 #endif
@@ -483,78 +633,15 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
     __syncthreads();
     // a warp runs as long as its first chain exists; its missing lanes (tail of the job) still take part in the
     // warp-cooperative perturbation stream but own no state
-    if (e - (threadIdx.x & 31) < chains) {
+    const long long warp_left = chains - (e - (threadIdx.x & 31));
+    if (warp_left > 0) {
         Draw<MODE> d;
         d.init(dv, e, env0 + e);
-        const float inv = sp.inv;
-        const bool flips = inv <= 0.f;
-        // PHILOX perturbation: ONE Bernoulli(p) renewal process per group of 32 consecutive chains over the interleaved
-        // index c = node*32 + lane (window = 32*n positions per iteration).  Each round every lane draws one geometric
-        // gap from its own stream, a warp prefix sum turns the 32 gaps into 32 event positions, and an event inside the
-        // current window flips bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n independent
-        // Bernoulli(p) per chain per iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
-        const u32 lane = threadIdx.x & 31u;
-        const u32 W = n * 32u;
-        u32 evp = 0xFFFFFFFFu;  // this lane's pending event, relative to the window start (none)
-        u32 last_p1 = 0;        // (position of the last generated event) + 1, relative to the window start
-        u32 *warp_cols = sst + (threadIdx.x & ~31u);
-        const long long warp_left = chains - (e - lane);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
-        int cur = active ? ssd_bucket(sp, s_tgt, st) : 0;
-        u32 run = 0;
-        for (int t = 0; t < iters; t++) {
-            if (active) {
-                const int b = ssd_bucket(sp, s_tgt, st);
-                if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
-                    if (sp.smem_hist) atomicAdd(&shist[cur], run);
-                    else atomicAdd(&hist[cur], (unsigned long long)run);
-                    cur = b; run = 0;
-                }
-                run++;
-            }
-            if constexpr (MODE == PBN_DRAW_REPLAY) {
-                if (active)
-                    for (u32 j = 0; j < n; j++)
-                        if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
-            } else {
-                if (flips) {
-                    for (;;) {
-                        if (evp < W) {
-                            const u32 tl = evp & 31u, bit = evp >> 5;
-                            if (tl < nvalid) atomicXor(warp_cols + tl + (bit >> 5) * PBN_BLOCK, 1u << (bit & 31u));
-                            evp = 0xFFFFFFFFu;
-                        }
-                        if (last_p1 > W) break;  // the last generated event lies beyond this window
-                        u32 pre = 1u + geom_gap(d.next(), inv);
-#pragma unroll
-                        for (int off = 1; off < 32; off <<= 1) {
-                            const u32 o = __shfl_up_sync(0xFFFFFFFFu, pre, off);
-                            if (lane >= (u32)off) pre += o;
-                        }
-                        evp = last_p1 - 1u + pre;
-                        last_p1 = __shfl_sync(0xFFFFFFFFu, evp, 31) + 1u;
-                    }
-                    if (evp != 0xFFFFFFFFu) evp -= W;
-                    last_p1 -= W;
-                    __syncwarp();
-                }
-            }
-            if (active) {
-                micro_step<NET, MODE, TQ>(nv, blob, st, d);  // env.step(0): pbn_target.py:269-271
-                if constexpr (HAS_ENV) {
-                    if (!ev.force) {
-                        int in = 1;
-                        while (in < ev.max_inner && !is_attracting(ev, att_off, cubes, st, w32)) { micro_step<NET, MODE, TQ>(nv, blob, st, d); in++; }
-                    }
-                }
-            }
-            if constexpr (MODE == PBN_DRAW_PHILOX) __syncwarp();  // updates land before the next iteration's cross-lane flips
-        }
+        SsdLoopArgs a{nv, ev, sp, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid};
+        if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d);   // every lane owns a chain: no predication
+        else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d);
         if (active) {
-            if (run) {
-                if (sp.smem_hist) atomicAdd(&shist[cur], run);
-                else atomicAdd(&hist[cur], (unsigned long long)run);
-            }
             store_state(st, state, chains, e, w32);
             d.done(dv, e);
         }
@@ -642,10 +729,11 @@ static int set_smem(K kernel, size_t bytes) {
 static inline int block_for(long long) { return PBN_BLOCK; }  // columns use a compile-time word stride of PBN_BLOCK
 
 // kernels are instantiated per (network kind, draw source, threshold quads TQ); TQ = 1 covers predictor sets with
-// up to 5 predictors per node (every shipped *_5_* set), TQ = 0 reads the count at run time
+// up to 5 predictors per node (every shipped *_5_* set), TQ = 4 up to 17 (the 28_15 set), TQ = 0 reads the count at run time
 #define DISPATCH(NETKIND, MODE, TS, CALL)                                                        \
     do {                                                                                         \
         if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX && (TS) == 4) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX, 1); } \
+        else if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX && (TS) == 16) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX, 4); } \
         else if ((NETKIND) == PBN_NET_PRED && (MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_PRED, PBN_DRAW_PHILOX, 0); }         \
         else if ((NETKIND) == PBN_NET_PRED) { CALL(PBN_NET_PRED, PBN_DRAW_REPLAY, 0); }          \
         else if ((MODE) == PBN_DRAW_PHILOX) { CALL(PBN_NET_TT, PBN_DRAW_PHILOX, 0); }            \
@@ -695,12 +783,28 @@ extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
     const DrawView dv = make_draws(draws);
     const int block = block_for(B);
     const unsigned grid = (unsigned)((B + block - 1) / block);
+    const bool att = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
     const size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                                                          \
-    if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                                   \
-    k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state,   \
-                                                 reward, terminated, truncated, inner_steps, B, env0)
+    if (att) {                                                                                                    \
+        if (int rc = set_smem(k_env_step_att<NK, MD>, smem)) return rc;                                           \
+        /* persistent grid: as many blocks as stay resident, each owning a contiguous range of envs */            \
+        int dev = 0, sms = 0, bps = 0;                                                                            \
+        CK(cudaGetDevice(&dev));                                                                                  \
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                    \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD>, block, smem));             \
+        long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
+        if (pgrid > (long long)grid) pgrid = grid;                                                                \
+        const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
+        pgrid = (B + per_block - 1) / per_block;                                                                  \
+        k_env_step_att<NK, MD><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
+                                                         reward, terminated, truncated, inner_steps, B, env0, per_block); \
+    } else {                                                                                                      \
+        if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                               \
+        k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
+                                                     reward, terminated, truncated, inner_steps, B, env0);        \
+    }
     DISPATCH(nv.kind, dv.mode, 0, CALL);
 #undef CALL
     CK(cudaGetLastError());

@@ -18,7 +18,7 @@ typedef uint64_t u64;
 
 // ----------------------------------------------------------------------------------------------- views
 // Packed network image (what pbn_net_create builds).  All offsets are in bytes from `blob`.
-//   PRED: thr  u32 [N][ts]      cumulative 31-bit thresholds, padded with 0x80000000 (never <= r31)
+//   PRED: thr  u32 [N][4*tsq_stride]  cumulative 31-bit thresholds (ts used), padded with 0x80000000 (never <= r31)
 //         rec  uint2 [N][fmax]  .x = four u8 node indices (in0 | in1<<8 | in2<<16 | self<<24), .y = 16-bit LUT
 //   TT  : node uint2 [N]        .x = table offset, .y = in_off | k<<16
 //         in   u16 []           input node indices (first = MSB of the table index)
@@ -26,6 +26,7 @@ typedef uint64_t u64;
 struct NetView {
     int kind, n, first, w32;
     int ts, fmax;
+    int tsq_stride;  // quads per threshold row: odd, so that divergent LDS.128 reads spread over all 8 bank groups
     int blob_bytes;
     int off_thr, off_rec, off_node, off_in;
     const unsigned char *blob;  // device
@@ -82,11 +83,10 @@ struct Draw<PBN_DRAW_PHILOX> {
     u32 k0, k1, blk, c1, c2, c3;
     u32 b0, b1, b2, b3;
     int have;
-    u32 cnt;
     __device__ __forceinline__ void init(const DrawView &dv, long long /*local*/, long long env_id) {
         k0 = dv.seed_lo; k1 = dv.seed_hi;
         blk = 0; c1 = dv.epoch; c2 = (u32)env_id; c3 = (u32)((u64)env_id >> 32);
-        have = 0; cnt = 0;
+        have = 0;
         b0 = b1 = b2 = b3 = 0;
     }
     __device__ __forceinline__ u32 next() {
@@ -98,13 +98,30 @@ struct Draw<PBN_DRAW_PHILOX> {
         u32 r = b0;
         b0 = b1; b1 = b2; b2 = b3;
         have--;
-        cnt++;
         return r;
     }
+    __device__ __forceinline__ u32 consumed() const { return blk * 4u - (u32)have; }  // draws taken so far
     // uniform integer in [lo, lo+n): random.randint(lo, lo+n-1)
     __device__ __forceinline__ int randint(int lo, int n) { return lo + (int)__umulhi(next(), (u32)n); }
     __device__ __forceinline__ void done(const DrawView &dv, long long local) {
-        if (dv.used) { dv.used[2 * local] = cnt; dv.used[2 * local + 1] = 0; }
+        if (dv.used) { dv.used[2 * local] = consumed(); dv.used[2 * local + 1] = 0; }
+    }
+    // position of the stream = number of draws consumed; seek() re-creates the state at a position, so an env can be
+    // handed from one thread to another (block-level compaction of divergent inner loops)
+    __device__ __forceinline__ void tell(u32 &a, u32 &b) const { a = consumed(); b = 0; }
+    __device__ __forceinline__ void seek(const DrawView &dv, long long local, long long env_id, u32 a, u32 /*b*/) {
+        init(dv, local, env_id);
+        blk = a >> 2;
+        const u32 r = a & 3u;
+        if (r) {
+            u32 x0, x1, x2, x3;
+            philox4x32_10(blk, c1, c2, c3, k0, k1, x0, x1, x2, x3);
+            blk++;
+            have = 4 - (int)r;
+            b0 = r == 1 ? x1 : (r == 2 ? x2 : x3);
+            b1 = r == 1 ? x2 : x3;
+            b2 = x3;
+        }
     }
 };
 
@@ -122,6 +139,11 @@ struct Draw<PBN_DRAW_REPLAY> {
     __device__ __forceinline__ double dbl() { nd++; return *dp++; }
     __device__ __forceinline__ void done(const DrawView &dv, long long local) {
         if (dv.used) { dv.used[2 * local] = ni; dv.used[2 * local + 1] = nd; }
+    }
+    __device__ __forceinline__ void tell(u32 &a, u32 &b) const { a = (u32)ni; b = (u32)nd; }
+    __device__ __forceinline__ void seek(const DrawView &dv, long long local, long long env_id, u32 a, u32 b) {
+        init(dv, local, env_id);
+        ip += a; dp += b; ni = a; nd = b;
     }
 };
 
@@ -181,7 +203,7 @@ __device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char 
     if constexpr (MODE == PBN_DRAW_PHILOX) {
         u32 r = d.next() >> 1;
         const int nq = TQ > 0 ? TQ : (nv.ts >> 2);
-        const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * nq;
+        const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * nv.tsq_stride;
         j = 0;
 #pragma unroll
         for (int q = 0; q < nq; q++) {
@@ -195,9 +217,19 @@ __device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char 
         for (int k = q0; k < q1; k++)
             if (nv.pr_cum[k] > r) { j = k - q0; break; }
     }
-    uint2 rec = reinterpret_cast<const uint2 *>(blob + nv.off_rec)[i * nv.fmax + j];
-    u32 idx = (st.bit(rec.x & 0xFF) << 3) | (st.bit((rec.x >> 8) & 0xFF) << 2) | (st.bit((rec.x >> 16) & 0xFF) << 1) |
-              st.bit(rec.x >> 24);
+    const uint2 rec = reinterpret_cast<const uint2 *>(blob + nv.off_rec)[i * nv.fmax + j];
+    // four gathers: byte k of rec.x is a node index; its word sits (idx & 0xE0) << 5 bytes into the column and the
+    // funnel-style shift below only looks at the low 5 bits of its count, so no per-field masking is needed
+    const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
+    const char *base = reinterpret_cast<const char *>(st.s);
+    const u32 w0 = *reinterpret_cast<const u32 *>(base + ((p0 & 0xE0u) << 5));
+    const u32 w1 = *reinterpret_cast<const u32 *>(base + ((p1 & 0xE0u) << 5));
+    const u32 w2 = *reinterpret_cast<const u32 *>(base + ((p2 & 0xE0u) << 5));
+    const u32 w3 = *reinterpret_cast<const u32 *>(base + ((p3 & 0xE0u) << 5));
+    u32 idx = __funnelshift_r(w0, 0, p0) & 1u;
+    idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
     return (rec.y >> idx) & 1u;
 }
 
@@ -247,9 +279,21 @@ __device__ __forceinline__ void sync_step(const NetView &nv, const unsigned char
 // cubes: u32 [n_cubes][w32][2] = (care, value); a state matches iff (word & care) == value for every word.
 __device__ __forceinline__ bool cube_match(const u32 *cubes, int c, const Col &st, int w32) {
     const u32 *p = cubes + (size_t)c * w32 * 2;
-    bool ok = true;
-    for (int w = 0; w < w32; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
-    return ok;
+    // networks up to 256 nodes: branch-free (the step-until-attractor tail is latency-bound, branches cost more than
+    // the compares); larger ones: groups of 8 words with an early exit between groups (a full-care cube of a 1024-node
+    // network fails in its first group)
+    if (w32 <= 8) {
+        bool ok = true;
+        for (int w = 0; w < w32; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
+        return ok;
+    }
+    for (int w0 = 0; w0 < w32; w0 += 8) {
+        bool ok = true;
+        const int w1 = w0 + 8 < w32 ? w0 + 8 : w32;
+        for (int w = w0; w < w1; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
+        if (!ok) return false;
+    }
+    return true;
 }
 __device__ __forceinline__ bool match_range(const u32 *cubes, int c0, int c1, const Col &st, int w32) {
     for (int c = c0; c < c1; c++)

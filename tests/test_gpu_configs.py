@@ -1,0 +1,124 @@
+"""GPU: the BASELINE.json configurations as parity cases at (or near) their full sizes, CUDA vs oracle, Philox mode."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle as orc  # noqa: E402
+from golden_util import cubes_to_attractors, load, synthetic_pbcn  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gym_PBN.b200 import abi, compiler, engine
+
+    class E:
+        pass
+
+    e = E()
+    e.abi, e.compiler, e.engine = abi, compiler, engine
+    return e
+
+
+def test_config2_bittner28_65536_lockstep_envs(eng):
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    net = eng.engine.Network(eng.compiler.load_bittner("28_15_median"))
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    B, seed = 65536, 2
+    env = eng.engine.EnvImage(net, eng.abi.ENV_TARGET, attractors=atts, horizon=100, max_inner=256)
+    oenv = orc.Env(orc.ENV_TARGET, 28, attractors=atts, horizon=100, max_inner=256)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost, ons, ota = np.zeros((B, 28), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    rng = np.random.default_rng(2)
+    for t in range(6):
+        act = rng.integers(0, 29, size=(B, 1)).astype(np.int32)
+        sim.env_step(env, torch.from_numpy(act))
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + t))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.inner.cpu().numpy(), inner)
+        assert np.array_equal(sim.terminated.cpu().numpy(), term)
+
+
+def test_config4_bittner200_multi_attractor_path(eng):
+    net = eng.engine.Network(eng.compiler.load_bittner("200_5_kmeans"))
+    sets, ids = orc.load_bittner("200_5_kmeans")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    n, B, seed = net.n, 8192, 4
+    assert n == 199
+    rng = np.random.default_rng(4)
+    atts = []
+    for a in range(4):
+        c = ["*"] * n
+        for i in rng.choice(n, size=4, replace=False):
+            c[i] = int(rng.integers(0, 2))
+        atts.append([tuple(c)])
+    env = eng.engine.EnvImage(net, eng.abi.ENV_MULTI, attractors=atts, horizon=100, max_inner=4096, dedup=True)
+    oenv = orc.Env(orc.ENV_MULTI, n, attractors=atts, horizon=100, max_inner=4096, dedup=1)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost, ons, ota = np.zeros((B, n), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+    for t in range(4):
+        act = rng.integers(0, n + 1, size=(B, 3)).astype(np.int32)
+        act[rng.random(B) < 0.25, 1] = 0
+        sim.env_step(env, torch.from_numpy(act))
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + t))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(sim.unpack(sim.obs_state).cpu().numpy(), obs)
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.inner.cpu().numpy(), inner)
+    assert inner.max() > 1  # the step-until-attractor loop actually ran
+
+
+@pytest.mark.parametrize("control_write", [False, True])
+def test_config5_synthetic_pbcn_1024_variable_durations(eng, control_write):
+    data = synthetic_pbcn()
+    net = eng.engine.Network(eng.compiler.compile_pbn_data(data))
+    onet = orc.net_from_pbn_data(data)
+    n, M, B, seed = 1024, 8, 2048, 9
+    assert net.w32 == 32
+    rng = np.random.default_rng(1)
+    targets = [tuple(int(v) for v in rng.integers(0, 2, n)) for _ in range(4)]
+    atts = [[t] for t in targets]
+    env = eng.engine.EnvImage(net, eng.abi.ENV_PBCN_SD, attractors=atts, targets=targets[:2], n_control=M,
+                              control_write=control_write, successful_reward=10, wrong_attractor_cost=2)
+    oenv = orc.Env(orc.ENV_PBCN_SD, n, attractors=atts, targets=targets[:2], n_control=M, control_write=int(control_write),
+                   successful_reward=10, wrong_attractor_cost=2)
+    st0 = rng.integers(0, 2, size=(B, n)).astype(np.uint8)
+    st0[:, 0] = 0
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    sim.set_state(st0)
+    ost, ons, ota = st0.copy(), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    for t in range(3):
+        act = np.concatenate([rng.integers(1, 65, (B, 1)), rng.integers(0, 2, (B, M))], 1).astype(np.int32)  # interval ~ U{1..64}
+        sim.env_step(env, torch.from_numpy(act))
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=t))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.inner.cpu().numpy(), act[:, 0])
+    if control_write:
+        # node 0 is never updated (randint(1, N-1)), so it holds the control bit written before the last update;
+        # control nodes 1..M-1 can be picked for update and then fall to 0 (their table is P = 0)
+        assert np.array_equal(ost[:, 0], act[:, 1].astype(np.uint8))
+
+
+def test_large_truth_table_rollout_and_sync(eng):
+    data = synthetic_pbcn(n=1024, m=8, seed=3)
+    net = eng.engine.Network(eng.compiler.compile_pbn_data(data))
+    onet = orc.net_from_pbn_data(data)
+    B, seed = 777, 5
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0))
+    sim.rollout(500)
+    orc.rollout(onet, ost, 500, orc.Draws(seed=seed, epoch=1))
+    assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+    sim.rollout(2, sync=True)
+    orc.rollout(onet, ost, 2, orc.Draws(seed=seed, epoch=2), sync=True)
+    assert np.array_equal(sim.unpack().cpu().numpy(), ost)
