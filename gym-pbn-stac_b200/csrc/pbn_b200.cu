@@ -244,6 +244,105 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
     d.done(dv, e);
 }
 
+// ----------------------------------------------------------------------------------------------- reset
+// One env's reset, on global memory (used by k_env_reset and by the fused vector step).
+//   TARGET: pbn_target.py:328-352 — sample(all_attractors, 2), a cube of each, '*' -> randint(0,1) position by position
+//   MULTI : pbn_target_multi.py:227-259 — first attractor -> last attractor (Q14)
+//   PBN family: pbn_env.py:190-213 — an attractor with <= 10 states, a uniform state of it, state[0] = 0 (common/pbn.py:77)
+template <int MODE>
+__device__ __forceinline__ void reset_env(const NetView &nv, const EnvView &ev, const DrawView &dv, u32 *state, int *n_steps,
+                                          int *target_att, u32 *target_state, long long B, long long e, long long env0) {
+    const int *att_off = reinterpret_cast<const int *>(ev.img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(ev.img + ev.off_cubes);
+    const int n = nv.n, w32 = nv.w32;
+    Draw<MODE> d;
+    d.init(dv, e, env0 + e);
+    if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
+        const int A = ev.n_att;
+        int a, b;
+        if (ev.kind == PBN_ENV_TARGET) {  // random.sample(all_attractors, 2), pbn_target.py:333
+            if constexpr (MODE == PBN_DRAW_REPLAY) { a = d.randint(0, A); b = d.randint(0, A); }
+            else { a = d.randint(0, A); b = d.randint(0, A - 1); if (b >= a) b++; }
+        } else { a = 0; b = A - 1; }  // first -> last (pbn_target_multi.py:237-238)
+        const int cs = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
+        const int ct = att_off[b] + d.randint(0, att_off[b + 1] - att_off[b]);
+        const u32 *ps = cubes + (size_t)cs * w32 * 2, *pt = cubes + (size_t)ct * w32 * 2;
+        u32 sw = 0, tw = 0;
+        for (int i = 0; i < n; i++) {  // '*' -> randint(0,1), state then target, position by position (:336-340)
+            const int w = i >> 5, bit = i & 31;
+            u32 sv = ((ps[2 * w] >> bit) & 1u) ? ((ps[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
+            u32 tv = ((pt[2 * w] >> bit) & 1u) ? ((pt[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
+            sw |= sv << bit; tw |= tv << bit;
+            if (bit == 31 || i == n - 1) {
+                state[(long long)w * B + e] = sw;
+                if (target_state) target_state[(long long)w * B + e] = tw;
+                sw = tw = 0;
+            }
+        }
+        target_att[e] = b;
+        n_steps[e] = 0;
+    } else {
+        int a;
+        do { a = d.randint(0, ev.n_att); } while (att_off[a + 1] - att_off[a] > 10);
+        const int c = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
+        const u32 *p = cubes + (size_t)c * w32 * 2;
+        for (int w = 0; w < w32; w++) state[(long long)w * B + e] = (w == 0) ? (p[1] & ~1u) : p[2 * w + 1];
+        if (n_steps) n_steps[e] = 0;
+    }
+    d.done(dv, e);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PBN_BLOCK) k_env_reset(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+                                                         int *target_att, u32 *target_state, const unsigned char *mask,
+                                                         long long B, long long env0) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B || (mask && !mask[e])) return;
+    reset_env<MODE>(nv, ev, dv, state, n_steps, target_att, target_state, B, e, env0);
+}
+
+// Vector-env epilogue of one finished env.step (fused into the step kernels): episode bookkeeping, block-aggregated
+// statistics, and — when the episode ended and autoreset is on — the reset, drawn from its own epoch so that the
+// fused launch is bit-identical to "step launch, then masked reset launch".
+struct VecView {
+    int enabled, autoreset;
+    long long *ep_return;
+    int *ep_len;
+    unsigned long long *stats;  // [6] episodes, return sum, length sum, successes, cap hits, env steps
+    u32 *final_obs, *target_state;
+    DrawView rdv;
+};
+template <int MODE>
+__device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev, const VecView &vx, unsigned long long *s_stats,
+                                           u32 *state, int *n_steps, int *target_att, u32 *obs_state, long long B,
+                                           long long e, long long env0, int rew, int tm, int tr, int in) {
+    const long long ret = vx.ep_return[e] + rew;
+    const int len = vx.ep_len[e] + 1;
+    atomicAdd(&s_stats[5], 1ULL);
+    if (tm) atomicAdd(&s_stats[3], 1ULL);
+    if ((ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) && in >= ev.max_inner) atomicAdd(&s_stats[4], 1ULL);
+    if (vx.final_obs)
+        for (int w = 0; w < nv.w32; w++) vx.final_obs[(long long)w * B + e] = obs_state[(long long)w * B + e];
+    if (tm | tr) {
+        atomicAdd(&s_stats[0], 1ULL);
+        atomicAdd(&s_stats[1], (unsigned long long)ret);  // two's complement: sums of negative returns wrap correctly
+        atomicAdd(&s_stats[2], (unsigned long long)len);
+        vx.ep_return[e] = 0;
+        vx.ep_len[e] = 0;
+        if (vx.autoreset) {
+            reset_env<MODE>(nv, ev, vx.rdv, state, n_steps, target_att, vx.target_state, B, e, env0);
+            for (int w = 0; w < nv.w32; w++) obs_state[(long long)w * B + e] = state[(long long)w * B + e];  // reset envs observe their new state
+        }
+    } else {
+        vx.ep_return[e] = ret;
+        vx.ep_len[e] = len;
+    }
+}
+__device__ __forceinline__ void vec_flush_stats(const VecView &vx, unsigned long long *s_stats) {
+    __syncthreads();
+    if (vx.enabled && threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&vx.stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
 // ----------------------------------------------------------------------------------------------- K2 env step
 __device__ __forceinline__ bool is_attracting(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, int w32) {
     if (ev.n_att == 0) return true;
@@ -262,12 +361,14 @@ template <int NET, int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
                                                         int *reward, unsigned char *terminated, unsigned char *truncated,
-                                                        int *inner_steps, long long B, long long env0) {
+                                                        int *inner_steps, long long B, long long env0, VecView vx) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    __shared__ unsigned long long s_stats[6];
     stage(blob, nv.blob, nv.blob_bytes);
     stage(img, ev.img, ev.img_bytes);
+    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,7 +377,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     Col ob{sst + w32 * PBN_BLOCK + threadIdx.x};
     if (e < B) load_state(st, state, B, e, w32);
     __syncthreads();
-    if (e >= B) return;
+    if (e < B) {
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
     const int *act = actions + e * K;
@@ -326,6 +427,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     truncated[e] = (unsigned char)tr;
     if (inner_steps) inner_steps[e] = in;
     d.done(dv, e);
+    if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, nullptr, obs_state, B, e, env0, rew, tm, tr, in);
+    }
+    vec_flush_stats(vx, s_stats);
 }
 
 // K2 for the two step-until-attractor envs (PBNTargetEnv, PBNTargetMultiEnv).  The inner loop is unbounded in the
@@ -338,14 +442,17 @@ template <int NET, int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
-                                                            int *inner_steps, long long B, long long env0, long long per_block) {
+                                                            int *inner_steps, long long B, long long env0, long long per_block,
+                                                            VecView vx) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
     const int w32 = nv.w32;
     __shared__ int s_next;
+    __shared__ unsigned long long s_stats[6];
     stage(blob, nv.blob, nv.blob_bytes);
     stage(img, ev.img, ev.img_bytes);
+    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long lo = (long long)blockIdx.x * per_block;
@@ -410,60 +517,16 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
             if (obs_state) store_state(multi ? ob : st, obs_state, B, e, w32);
             reward[e] = rew;
             terminated[e] = (unsigned char)tm;
-            truncated[e] = (unsigned char)(n_steps[e] == ev.horizon);
+            const int tr = (n_steps[e] == ev.horizon);
+            truncated[e] = (unsigned char)tr;
             if (inner_steps) inner_steps[e] = in;
             d.done(dv, e);
+            if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, const_cast<int *>(target_att), obs_state, B, e, env0, rew, tm, tr, in);
             have = false;
             nxt = lo + atomicAdd(&s_next, 1);
         }
     }
-}
-
-// ----------------------------------------------------------------------------------------------- reset
-template <int MODE>
-__global__ void __launch_bounds__(PBN_BLOCK) k_env_reset(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
-                                                         int *target_att, u32 *target_state, const unsigned char *mask,
-                                                         long long B, long long env0) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B || (mask && !mask[e])) return;
-    const int *att_off = reinterpret_cast<const int *>(ev.img);
-    const u32 *cubes = reinterpret_cast<const u32 *>(ev.img + ev.off_cubes);
-    const int n = nv.n, w32 = nv.w32;
-    Draw<MODE> d;
-    d.init(dv, e, env0 + e);
-    if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
-        const int A = ev.n_att;
-        int a, b;
-        if (ev.kind == PBN_ENV_TARGET) {  // random.sample(all_attractors, 2), pbn_target.py:333
-            if constexpr (MODE == PBN_DRAW_REPLAY) { a = d.randint(0, A); b = d.randint(0, A); }
-            else { a = d.randint(0, A); b = d.randint(0, A - 1); if (b >= a) b++; }
-        } else { a = 0; b = A - 1; }  // first -> last (pbn_target_multi.py:237-238)
-        const int cs = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
-        const int ct = att_off[b] + d.randint(0, att_off[b + 1] - att_off[b]);
-        const u32 *ps = cubes + (size_t)cs * w32 * 2, *pt = cubes + (size_t)ct * w32 * 2;
-        u32 sw = 0, tw = 0;
-        for (int i = 0; i < n; i++) {  // '*' -> randint(0,1), state then target, position by position (:336-340)
-            const int w = i >> 5, bit = i & 31;
-            u32 sv = ((ps[2 * w] >> bit) & 1u) ? ((ps[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
-            u32 tv = ((pt[2 * w] >> bit) & 1u) ? ((pt[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
-            sw |= sv << bit; tw |= tv << bit;
-            if (bit == 31 || i == n - 1) {
-                state[(long long)w * B + e] = sw;
-                if (target_state) target_state[(long long)w * B + e] = tw;
-                sw = tw = 0;
-            }
-        }
-        target_att[e] = b;
-        n_steps[e] = 0;
-    } else {  // pbn_env.py:201-206: an attractor with <= 10 states, a uniform state of it; PBN.reset forces state[0] = 0
-        int a;
-        do { a = d.randint(0, ev.n_att); } while (att_off[a + 1] - att_off[a] > 10);
-        const int c = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
-        const u32 *p = cubes + (size_t)c * w32 * 2;
-        for (int w = 0; w < w32; w++) state[(long long)w * B + e] = (w == 0) ? (p[1] & ~1u) : p[2 * w + 1];
-        if (n_steps) n_steps[e] = 0;
-    }
-    d.done(dv, e);
+    vec_flush_stats(vx, s_stats);
 }
 
 template <int MODE>
@@ -767,10 +830,10 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
     return PBN_OK;
 }
 
-extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
-                            const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
-                            uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
-                            void *stream) {
+static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                         const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
+                         uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
+                         const PbnVecState *vec, void *stream) {
     if (!env || !state || !actions || !reward || !terminated || !truncated || B < 0 || K < 1) return fail(PBN_ERR_ARG, "bad argument");
     if ((env->v.kind == PBN_ENV_TARGET || env->v.kind == PBN_ENV_MULTI) && (!n_steps || !target_att))
         return fail(PBN_ERR_ARG, "target envs need n_steps and target_att");
@@ -781,6 +844,21 @@ extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
     const NetView &nv = env->net->v;
     const EnvView &ev = env->v;
     const DrawView dv = make_draws(draws);
+    VecView vx;
+    memset(&vx, 0, sizeof vx);
+    if (vec) {
+        if (!vec->ep_return || !vec->ep_len || !vec->stats || !obs_state) return fail(PBN_ERR_ARG, "vector step needs ep_return, ep_len, stats and obs_state");
+        if (vec->autoreset) {
+            if (int rc = check_draws(&vec->reset_draws)) return rc;
+            const bool tgt = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
+            if (ev.n_att < (ev.kind == PBN_ENV_TARGET ? 2 : 1)) return fail(PBN_ERR_ARG, "autoreset needs attractors");
+            if (tgt && !vec->target_state) return fail(PBN_ERR_ARG, "autoreset of target envs needs target_state");
+            vx.rdv = make_draws(&vec->reset_draws);
+        }
+        vx.enabled = 1; vx.autoreset = vec->autoreset;
+        vx.ep_return = (long long *)vec->ep_return; vx.ep_len = vec->ep_len; vx.stats = (unsigned long long *)vec->stats;
+        vx.final_obs = vec->final_obs; vx.target_state = vec->target_state;
+    }
     const int block = block_for(B);
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const bool att = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
@@ -799,16 +877,33 @@ extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
         const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
         pgrid = (B + per_block - 1) / per_block;                                                                  \
         k_env_step_att<NK, MD><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                         reward, terminated, truncated, inner_steps, B, env0, per_block); \
+                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, vx); \
     } else {                                                                                                      \
         if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                               \
         k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                     reward, terminated, truncated, inner_steps, B, env0);        \
+                                                     reward, terminated, truncated, inner_steps, B, env0, vx);    \
     }
     DISPATCH(nv.kind, dv.mode, 0, CALL);
 #undef CALL
     CK(cudaGetLastError());
     return PBN_OK;
+}
+
+extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                            const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
+                            uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
+                            void *stream) {
+    return env_step_impl(env, state, n_steps, target_att, actions, K, obs_state, reward, terminated, truncated, inner_steps, B,
+                         env0, draws, nullptr, stream);
+}
+
+extern "C" int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
+                            int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
+                            int32_t *inner_steps, const PbnVecState *vec, int64_t B, int64_t env0, const PbnDraws *draws,
+                            void *stream) {
+    if (!vec) return fail(PBN_ERR_ARG, "vec is null");
+    return env_step_impl(env, state, n_steps, target_att, actions, K, obs_state, reward, terminated, truncated, inner_steps, B,
+                         env0, draws, vec, stream);
 }
 
 extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,

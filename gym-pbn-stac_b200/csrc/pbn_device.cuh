@@ -279,20 +279,15 @@ __device__ __forceinline__ void sync_step(const NetView &nv, const unsigned char
 // cubes: u32 [n_cubes][w32][2] = (care, value); a state matches iff (word & care) == value for every word.
 __device__ __forceinline__ bool cube_match(const u32 *cubes, int c, const Col &st, int w32) {
     const u32 *p = cubes + (size_t)c * w32 * 2;
-    // networks up to 256 nodes: branch-free (the step-until-attractor tail is latency-bound, branches cost more than
-    // the compares); larger ones: groups of 8 words with an early exit between groups (a full-care cube of a 1024-node
-    // network fails in its first group)
+    // networks up to 256 nodes: branch-free (the step-until-attractor tail is latency-bound, branches cost more than the
+    // compares); larger ones: early exit per word (a full-care cube of a 1024-node network fails in its first word)
     if (w32 <= 8) {
         bool ok = true;
         for (int w = 0; w < w32; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
         return ok;
     }
-    for (int w0 = 0; w0 < w32; w0 += 8) {
-        bool ok = true;
-        const int w1 = w0 + 8 < w32 ? w0 + 8 : w32;
-        for (int w = w0; w < w1; w++) ok &= ((st.word(w) & p[2 * w]) == p[2 * w + 1]);
-        if (!ok) return false;
-    }
+    for (int w = 0; w < w32; w++)
+        if ((st.word(w) & p[2 * w]) != p[2 * w + 1]) return false;
     return true;
 }
 __device__ __forceinline__ bool match_range(const u32 *cubes, int c0, int c1, const Col &st, int w32) {

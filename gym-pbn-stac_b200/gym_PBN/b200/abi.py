@@ -36,6 +36,11 @@ class PbnDraws(C.Structure):
                 ("used", C.c_void_p)]
 
 
+class PbnVecState(C.Structure):
+    _fields_ = [("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("stats", C.c_void_p), ("final_obs", C.c_void_p),
+                ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "pbn_net_create": (C.c_int, [C.POINTER(PbnNetDesc), C.POINTER(C.c_void_p)]),
@@ -47,6 +52,9 @@ EXPORTS = {
                               C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                               C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_vec_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PbnVecState), C.c_int64, C.c_int64,
                                C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),

@@ -123,8 +123,8 @@ class Simulator:
         self.target_state = torch.zeros((net.w32, self.B), dtype=torch.int32, device=self.device)
         self.obs_state = torch.zeros((net.w32, self.B), dtype=torch.int32, device=self.device)
         self.reward = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-        self.terminated = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
-        self.truncated = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        self.terminated = torch.zeros(self.B, dtype=torch.bool, device=self.device)  # 1-byte 0/1, written by the kernels
+        self.truncated = torch.zeros(self.B, dtype=torch.bool, device=self.device)
         self.inner = torch.zeros(self.B, dtype=torch.int32, device=self.device)
         self.launches = 0
 
@@ -181,6 +181,21 @@ class Simulator:
                                              _ptr(actions), actions.shape[1], _ptr(self.obs_state), _ptr(self.reward),
                                              _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner), self.B,
                                              self.env0, C.byref(d), _stream()))
+            self.launches += 1
+
+    def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True):
+        """Fused vector-env step (one launch): env.step for every env + episode bookkeeping + statistics + reset of the envs
+        that finished.  Consumes two epochs (step, reset) exactly like env_step followed by a masked env_reset."""
+        actions = actions.to(self.device, dtype=torch.int32).reshape(self.B, -1).contiguous()
+        d = self._draws()
+        rd = self._draws()
+        v = abi.PbnVecState(ep_return=_ptr(ep_return), ep_len=_ptr(ep_len), stats=_ptr(stats), final_obs=_ptr(final_obs),
+                            target_state=_ptr(self.target_state), autoreset=int(bool(autoreset)), reset_draws=rd)
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_vec_step(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                             _ptr(actions), actions.shape[1], _ptr(self.obs_state), _ptr(self.reward),
+                                             _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner), C.byref(v),
+                                             self.B, self.env0, C.byref(d), _stream()))
             self.launches += 1
 
     def env_reset(self, env: EnvImage, mask=None, replay=None):

@@ -1,8 +1,8 @@
 """PBNVectorEnv — `num_envs` lockstep copies of one gym_PBN env on one GPU, everything resident on the device.
 
 The reference has no vectorised env (one Python object per env).  Here one CUDA launch performs
-`env.step` for every env: interventions, update(s) until attracting (capped), reward / terminated / truncated; a second
-launch resets the envs that finished.  Observations, rewards and flags are torch tensors on the device, owned by the
+`env.step` for every env — interventions, update(s) until attracting (capped), reward / terminated / truncated — and, in
+the same launch (pbn_vec_step), the episode bookkeeping, the statistics and the reset of the envs that finished.  Observations, rewards and flags are torch tensors on the device, owned by the
 env and overwritten by the next `step` (clone them to keep them).
 
 Multi-GPU: one process per GPU; pass `global_num_envs` and the env ids are sharded over ranks
@@ -105,30 +105,12 @@ class PBNVectorEnv:
         if actions.shape[1] != self.action_width:
             raise ValueError(f"actions must have shape [{self.num_envs}, {self.action_width}]")
         sim = self.sim
-        sim.env_step(self.image, actions)
-        done = (sim.terminated | sim.truncated)
-        self.ep_return += sim.reward
-        self.ep_len += 1
-        n_done = done.sum()
-        st = self.stats.v
-        st[0] += n_done
-        st[1] += (self.ep_return * done).sum()
-        st[2] += (self.ep_len * done).sum()
-        st[3] += sim.terminated.sum()
-        st[4] += (sim.inner >= self.max_inner_steps).sum() if self.family != "pbn" else 0
-        st[5] += self.num_envs
-        obs_planes = sim.obs_state
-        info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state}
-        if self.autoreset:
-            self.final_obs.copy_(sim.obs_state)
-            info["final_obs_packed"] = self.final_obs
-            sim.env_reset(self.image, mask=done)
-            keep = (1 - done).to(torch.int64)
-            self.ep_return *= keep
-            self.ep_len *= keep.to(torch.int32)
-            # envs that were reset observe their new state; the others keep the step's observation
-            obs_planes = torch.where(done.bool().unsqueeze(0), sim.state, sim.obs_state)
-        return self._obs(obs_planes), sim.reward, sim.terminated.bool(), sim.truncated.bool(), info
+        # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)
+        sim.vec_step(self.image, actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
+                     autoreset=self.autoreset)
+        info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state, "final_obs_packed": self.final_obs}
+        # after the launch obs_state holds the step's observation, or the NEW state for envs that were auto-reset
+        return self._obs(sim.obs_state), sim.reward, sim.terminated, sim.truncated, info
 
     def step_host(self, actions_host):
         """Host in / host out convenience (pinned staging): NumPy actions -> NumPy (obs, reward, terminated, truncated)."""

@@ -120,6 +120,24 @@ int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int
                  const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
                  uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
 
+/* Vector-env step: K2 plus, in the same launch, the bookkeeping a batched env needs — running episode return/length,
+   block-aggregated statistics (episodes, return sum, length sum, successes, inner-cap hits, env steps; accumulated into
+   stats[6]), the step's observation copied to final_obs, and for finished envs the reset (reset_draws, its own epoch), after
+   which obs_state holds the NEW state of those envs.  Bit-identical to pbn_env_step followed by a masked pbn_env_reset.
+   The reference has no vector env; this serves gym_PBN.b200.vector_env.PBNVectorEnv.step. */
+typedef struct {
+    int64_t *ep_return;     /* [B] */
+    int32_t *ep_len;        /* [B] */
+    int64_t *stats;         /* [6] */
+    uint32_t *final_obs;    /* planes [W32][B], optional */
+    uint32_t *target_state; /* planes [W32][B], written on reset (target envs) */
+    int32_t autoreset;
+    PbnDraws reset_draws;
+} PbnVecState;
+int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
+                 int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
+                 int32_t *inner_steps, const PbnVecState *vec, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
 /* reset of the envs selected by mask (NULL = all): PBNTargetEnv.reset pbn_target.py:328-352,
    PBNTargetMultiEnv.reset pbn_target_multi.py:227-259, PBNEnv.reset pbn_env.py:190-213 (+ PBN.reset common/pbn.py:55-78). */
 int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,

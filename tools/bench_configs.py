@@ -75,6 +75,26 @@ def main():
     sim.env_reset(env1)
     t = timed(lambda: sim.env_step(env1, acts), reps=50)
     out.append({"config": "Bittner-28 PBN-target-v0, 65536 envs, all-attracting, 1 launch/step", "env_steps_per_s": B / t, "ms_per_step": t * 1e3})
+    # the same through the public PBNVectorEnv.step (fused launch + unpack), wall clock, device-resident actions
+    import time
+
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    genv = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=[[("*",) * 28], [("*",) * 28]], max_inner_steps=1)
+    for obs_mode in ("bits", "packed"):
+        vec = PBNVectorEnv(genv, 65536, seed=1, obs=obs_mode)
+        vec.reset()
+        for _ in range(20):
+            vec.step(acts)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            vec.step(acts)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / 200
+        out.append({"config": f"PBNVectorEnv.step wall clock, Bittner-28, 65536 envs, all-attracting, obs={obs_mode}",
+                    "env_steps_per_s": 65536 / t, "us_per_step": t * 1e6})
     # configs[3]: Bittner-200 target_multi, attractor path, 131 072 envs per GPU
     net = engine.Network(compiler.load_bittner("200_5_kmeans"))
     B = 131072
