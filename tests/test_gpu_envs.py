@@ -260,3 +260,30 @@ def test_compute_ssd_hist_drop_in():
     z = load("b100_ssd_long.npz")
     floor = total_variation(z["ssd"][0], z["ssd"][1])
     assert total_variation(vals, z["ssd"][0]) <= 3 * floor
+
+
+def test_abi_error_paths():
+    """Errors are status codes at the C boundary and the reference's exception types above it."""
+    from gym_PBN.b200 import abi, compiler, engine
+
+    net = engine.Network(compiler.load_bittner("28_15_median"))
+    sim = engine.Simulator(net, 64, seed=1)
+    with pytest.raises(ValueError):  # target node out of range
+        sim.ssd(10, 0.01, np.array([0, 99], np.int32))
+    with pytest.raises(ValueError):  # invalid bit flip probability (utils/eval.py:31-33)
+        sim.ssd(10, 1.5, np.array([0, 1], np.int32))
+    with pytest.raises(ValueError):  # TARGET reset needs two attractors (random.sample(..., 2))
+        img = engine.EnvImage(net, abi.ENV_TARGET, attractors=[[("*",) * 28]])
+        sim.env_reset(img)
+    with pytest.raises(ValueError):  # cube of the wrong length
+        engine.EnvImage(net, abi.ENV_TARGET, attractors=[[(0, 1)]])
+    with pytest.raises(ValueError):  # sampled-data action width
+        tt = engine.Network(compiler.compile_pbn_data([(np.array([False, True]), np.array([0.2, 0.9]), "a", False),
+                                                       (np.array([True, False]), np.array([0.5, 0.5]), "b", False)]))
+        s2 = engine.Simulator(tt, 4)
+        s2.env_step(engine.EnvImage(tt, abi.ENV_PBN_SD, attractors=[[(0, 0)]], targets=[(0, 1)]), torch.zeros((4, 1), dtype=torch.int32))
+    assert b"" == b"" and abi.lib().pbn_last_error() is not None
+    with pytest.raises(abi.PbnError):  # predictor networks are limited to 256 nodes
+        spec = compiler.load_bittner("28_15_median")
+        spec.n = 300
+        engine.Network(spec)
