@@ -251,7 +251,8 @@ def run_gpu(args):
             "thread_inst_per_iter": tipi, "inst_source": ipi.get("source"),
             "kernel_ms": t_kernel * 1e3,
             "iters_per_s_kernel": per_launch_iters / t_kernel,
-            "philox_blocks_per_s_peak": philox_peak,
+            "philox_blocks_per_s": 0.75 * per_launch_iters / t_kernel,  # 2 update draws + ~1 gap draw per iteration
+            "philox_blocks_per_s_peak": philox_peak, "philox_frac": 0.75 * per_launch_iters / t_kernel / philox_peak,
             "state_bytes_per_s": state_bytes / t_kernel,
             "traffic": ipi.get("dram_bytes_per_launch"),
             "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg / t_kernel / 1e9, "peak_gbs": hbm_peak,
