@@ -126,30 +126,39 @@ class PBN:
 
     def attractors(self, max_nodes=22):
         """Terminal strongly connected components of the asynchronous STG, as a list of sets of state tuples
-        (what PBNEnv.compute_attractors obtains from networkx, pbn_env.py:238-255).  Host-side, N <= max_nodes."""
+        (what PBNEnv.compute_attractors obtains from networkx, pbn_env.py:238-255).  Host-side and vectorised over all
+        2^N states; edges follow common/pbn.py:186-197 (node i can change value: p > 0 from 0, p < 1 from 1)."""
         from scipy.sparse import csr_matrix
         from scipy.sparse.csgraph import connected_components
 
         if self.N > max_nodes:
             raise ValueError(f"exhaustive attractor search is O(2^N); N={self.N} > {max_nodes}")
-        S = 2**self.N
-        weights = 1 << np.arange(self.N - 1, -1, -1)
+        N, S = self.N, 2**self.N
+        idx = np.arange(S, dtype=np.int64)
+        bit = lambda i: (idx >> (N - 1 - i)) & 1  # state index is MSB-first like booleanize()  # noqa: E731
         rows, cols = [], []
-        for idx in range(S):
-            s = booleanize(idx, self.N)
-            for nxt, _p in self.async_successors(s):
-                rows.append(idx)
-                cols.append(int(nxt.astype(np.int64) @ weights))
+        for i, node in enumerate(self.nodes):
+            inputs = np.nonzero(node.input_mask)[0]
+            tidx = np.zeros(S, dtype=np.int64)
+            for j in inputs:
+                tidx = (tidx << 1) | bit(j)
+            p = node.function.reshape(-1)[tidx]
+            cur = bit(i)
+            change = ((p > 0.0) & (cur == 0)) | ((p < 1.0) & (cur == 1))
+            src = idx[change]
+            rows.append(src)
+            cols.append(src ^ (1 << (N - 1 - i)))
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
         A = csr_matrix((np.ones(len(rows), np.int8), (rows, cols)), shape=(S, S))
         ncomp, label = connected_components(A, directed=True, connection="strong")
         leaves = np.ones(ncomp, bool)
-        for r, c in zip(rows, cols):
-            if label[r] != label[c]:
-                leaves[label[r]] = False
+        leaves[label[rows[label[rows] != label[cols]]]] = False  # a component with an edge leaving it is not terminal
         out = []
+        order = np.argsort(label, kind="stable")
+        bounds = np.searchsorted(label[order], np.arange(ncomp + 1))
         for comp in np.nonzero(leaves)[0]:
-            members = np.nonzero(label == comp)[0]
-            out.append({tuple(int(b) for b in booleanize(int(m), self.N)) for m in members})
+            members = order[bounds[comp]:bounds[comp + 1]]
+            out.append({tuple(int(b) for b in booleanize(int(m), N)) for m in members})
         return out
 
 

@@ -226,6 +226,36 @@ def gen_tt_core(ns, n=40, steps=400, seed=11):
     np.savez_compressed(GOLD / "tt40_core.npz", **out)
 
 
+def gen_attractors(ns, seed=17):
+    """PBNEnv.compute_attractors (exhaustive async STG + networkx attracting_components, pbn_env.py:238-255) on a few
+    random truth-table networks — pins the exhaustive attractor search."""
+    rng = np.random.default_rng(seed)
+    out = {"n_nets": 0}
+    for k, n in enumerate((5, 6, 7, 8, 9)):
+        pbn_data = []
+        for i in range(n):
+            kin = int(rng.integers(0, 4))
+            mask = np.zeros(n, bool)
+            mask[rng.choice(n, size=kin, replace=False)] = True
+            f1, f2 = rng.integers(0, 2, 2**kin), rng.integers(0, 2, 2**kin)
+            c = float(rng.choice([0.0, 0.3, 1.0]))
+            table = (c * f1 + (1 - c) * f2).reshape([2] * kin) if kin else np.array(float(rng.integers(0, 2)))
+            pbn_data.append((mask, table, i, f"G{i}", False))
+        with quiet():
+            pbn = ns.pbn.PBN(PBN_data=pbn_data)
+            env = ns.pbn_env.PBNEnv.__new__(ns.pbn_env.PBNEnv)
+            env.PBN = pbn
+            env.render_mode = "human"
+            atts = env.compute_attractors()
+        masks, tables = pbn_data_arrays(pbn_data)
+        flat = sorted(sorted(a) for a in atts)
+        out[f"n{k}/masks"], out[f"n{k}/tables"] = masks, tables
+        out[f"n{k}/att_sizes"] = np.array([len(a) for a in flat], np.int32)
+        out[f"n{k}/att_states"] = np.array([s for a in flat for s in a], np.int8).reshape(-1, n)
+        out["n_nets"] = k + 1
+    np.savez_compressed(GOLD / "tt_attractors.npz", **out)
+
+
 # ------------------------------------------------------------------------------------------ Bittner graph
 def gen_graph_core(ns, name, E, steps, sync_steps, seed):
     sets, ids = load_sets(name)
@@ -431,6 +461,7 @@ def main():
         "ex5": lambda: gen_ex5_pbnenv(ns),
         "pbcn": lambda: gen_ex5_pbcn_sampled(ns),
         "tt40": lambda: gen_tt_core(ns),
+        "attractors": lambda: gen_attractors(ns),
         "g28": lambda: gen_graph_core(ns, "28_15_median", E=3, steps=400, sync_steps=20, seed=7),
         "g100": lambda: gen_graph_core(ns, "100_5_kmeans", E=2, steps=400, sync_steps=10, seed=8),
         "g200": lambda: gen_graph_core(ns, "200_5_kmeans", E=1, steps=300, sync_steps=5, seed=9),

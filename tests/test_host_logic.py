@@ -175,3 +175,31 @@ def test_engine_fails_loudly_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(abi.PbnError):
         engine.Network(compiler.load_bittner("28_15_median"))
+
+
+def test_exhaustive_attractors_match_reference():
+    """PBN.attractors (vectorised terminal-SCC search) == the reference's compute_attractors on recorded networks.
+    Runs on the CPU: the attractor search is host code (constructor-time, not the step path)."""
+    import types
+
+    from gym_PBN.envs.common.node import Node
+    from gym_PBN.envs.common.pbn import PBN
+
+    z = load("tt_attractors.npz")
+    for k in range(int(z["n_nets"])):
+        masks, tables = z[f"n{k}/masks"], z[f"n{k}/tables"]
+        n = len(masks)
+        pbn = PBN.__new__(PBN)  # no device needed for the host-side search
+        pbn.N = n
+        pbn.nodes = np.empty(n, dtype=object)
+        for i in range(n):
+            kin = int(masks[i].sum())
+            pbn.nodes[i] = Node(masks[i], tables[i, : 2**kin], i)
+        got = sorted(sorted(a) for a in pbn.attractors())
+        sizes = z[f"n{k}/att_sizes"]
+        states = [tuple(int(v) for v in s) for s in z[f"n{k}/att_states"]]
+        want, pos = [], 0
+        for sz in sizes:
+            want.append(states[pos:pos + sz])
+            pos += sz
+        assert got == want, k
