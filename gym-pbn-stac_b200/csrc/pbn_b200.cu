@@ -1015,6 +1015,48 @@ extern "C" int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains
     return rc;
 }
 
+extern "C" int pbn_upload(void *dst_dev, const void *src_host, int64_t nbytes, void *stream) {
+    if (!dst_dev || !src_host || nbytes < 0) return fail(PBN_ERR_ARG, "bad argument");
+    CK(cudaMemcpyAsync(dst_dev, src_host, (size_t)nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return PBN_OK;
+}
+extern "C" int pbn_fetch_host(const void *const *src_dev, const int64_t *nbytes, int32_t n, void *dst_host, void *stream) {
+    if (!src_dev || !nbytes || !dst_host || n < 0) return fail(PBN_ERR_ARG, "bad argument");
+    char *dst = static_cast<char *>(dst_host);
+    for (int i = 0; i < n; i++) {  // one cudaMemcpyAsync per buffer (no batched-copy API)
+        CK(cudaMemcpyAsync(dst, src_dev[i], (size_t)nbytes[i], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        dst += nbytes[i];
+    }
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return PBN_OK;
+}
+
+__global__ void k_gather_step(const int *reward, const unsigned char *terminated, const unsigned char *truncated, const int *inner,
+                              const u32 *state, const u32 *obs, int w32, long long B, long long e, u32 *out) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        out[0] = (u32)reward[e];
+        out[1] = inner ? (u32)inner[e] : 0u;
+        out[2] = (u32)terminated[e] | ((u32)truncated[e] << 8);
+    }
+    for (int w = t; w < w32; w += blockDim.x) {
+        out[3 + w] = state[(long long)w * B + e];
+        out[3 + w32 + w] = obs ? obs[(long long)w * B + e] : 0u;
+    }
+}
+extern "C" int pbn_fetch_step_host(const int32_t *reward, const uint8_t *terminated, const uint8_t *truncated, const int32_t *inner,
+                                   const uint32_t *state, const uint32_t *obs_state, int32_t w32, int64_t B, int64_t e,
+                                   void *scratch_dev, void *dst_host, void *stream) {
+    if (!reward || !terminated || !truncated || !state || !scratch_dev || !dst_host || w32 < 1 || e < 0 || e >= B)
+        return fail(PBN_ERR_ARG, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_gather_step<<<1, 32, 0, s>>>(reward, terminated, truncated, inner, state, obs_state, w32, B, e, (u32 *)scratch_dev);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst_host, scratch_dev, (size_t)(12 + 8 * w32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return PBN_OK;
+}
+
 extern "C" int pbn_unpack_state(const uint32_t *state, int64_t B, int32_t n, uint8_t *out, void *stream) {
     if (!state || !out || B < 0 || n < 1) return fail(PBN_ERR_ARG, "bad argument");
     if (B == 0) return PBN_OK;

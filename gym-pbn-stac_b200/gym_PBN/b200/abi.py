@@ -65,6 +65,10 @@ EXPORTS = {
                                C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "pbn_unpack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_pack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pbn_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pbn_fetch_host": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
+    "pbn_fetch_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pbn_issue_peak": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "pbn_last_error": (C.c_char_p, []),
     "pbn_version": (C.c_char_p, []),

@@ -31,6 +31,8 @@ def require_cuda(device):
     device = torch.device(device if device is not None else "cuda")
     if device.type != "cuda" or not torch.cuda.is_available():
         raise abi.PbnError("gym_PBN (B200 build) needs a CUDA device; there is no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     return device
 
 

@@ -1,12 +1,13 @@
 """Shared plumbing of the single-env drop-in classes: one device `Simulator` with B = 1, kernel launches for
 `step`, host-typed return values (NumPy arrays / Python ints / bools) like the reference hands out."""
+import ctypes as C
 import os
 import random
 
 import numpy as np
 import torch
 
-from gym_PBN.b200 import engine
+from gym_PBN.b200 import abi, engine
 
 
 class DeviceEnvMixin:
@@ -34,13 +35,46 @@ class DeviceEnvMixin:
     def _invalidate_images(self):
         self._images = {}
 
+    def _single_io(self, K):
+        """Pinned host staging for the single env: actions up, {reward, flags, inner, state, obs} down in ONE read-back."""
+        io = getattr(self, "_io", None)
+        if io is None or io["K"] != K:
+            sim, w32 = self.sim, self.network.w32
+            host = torch.empty(12 + 8 * w32, dtype=torch.uint8).pin_memory()
+            acts_host = torch.empty(K, dtype=torch.int32).pin_memory()
+            io = {"K": K, "host": host, "np": host.numpy(), "acts_host": acts_host, "acts_np": acts_host.numpy(),
+                  "acts_dev": torch.empty((1, K), dtype=torch.int32, device=sim.device),
+                  "scratch": torch.empty(3 + 2 * w32, dtype=torch.int32, device=sim.device)}
+            p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+            io["step_args"] = lambda image, d, stream: (
+                image.handle, p(sim.state), p(sim.n_steps), p(sim.target_att), p(io["acts_dev"]), K, p(sim.obs_state),
+                p(sim.reward), p(sim.terminated), p(sim.truncated), p(sim.inner), 1, sim.env0, C.byref(d), stream)
+            io["fetch_args"] = (p(sim.reward), p(sim.terminated), p(sim.truncated), p(sim.inner), p(sim.state),
+                                p(sim.obs_state), w32, 1, 0, p(io["scratch"]), p(host))
+            io["up_args"] = (p(io["acts_dev"]), p(acts_host), 4 * K)
+            self._io = io
+        return io
+
     def _run_step(self, image, actions):
-        """One K2 launch for the single env -> (reward, terminated, truncated, inner_steps)."""
-        a = torch.as_tensor(np.asarray(actions, dtype=np.int32).reshape(1, -1))
-        self.sim.env_step(image, a)
-        out = torch.stack([self.sim.reward, self.sim.terminated.to(torch.int32), self.sim.truncated.to(torch.int32),
-                           self.sim.inner]).cpu().numpy()
-        return int(out[0, 0]), bool(out[1, 0]), bool(out[2, 0]), int(out[3, 0])
+        """One K2 launch for the single env and one read-back -> (reward, terminated, truncated, inner_steps);
+        the new state / observation bits are left in self._last_state / self._last_obs (uint8 [N])."""
+        acts = np.asarray(actions, dtype=np.int32).reshape(-1)
+        io = self._single_io(len(acts))
+        io["acts_np"][:] = acts
+        sim, lib = self.sim, abi.lib()
+        if torch.cuda.current_device() != sim.device.index:
+            torch.cuda.set_device(sim.device)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        d = sim._draws()
+        abi.check(lib.pbn_upload(*io["up_args"], stream))
+        abi.check(lib.pbn_env_step(*io["step_args"](image, d, stream)))
+        abi.check(lib.pbn_fetch_step_host(*io["fetch_args"], stream))
+        sim.launches += 2
+        buf, n, w4 = io["np"], self.network.n, 4 * self.network.w32
+        head = buf[:12].view(np.int32)
+        self._last_state = np.unpackbits(buf[12:12 + w4], bitorder="little")[:n]
+        self._last_obs = np.unpackbits(buf[12 + w4:12 + 2 * w4], bitorder="little")[:n]
+        return int(head[0]), bool(head[2] & 0xFF), bool((head[2] >> 8) & 0xFF), int(head[1])
 
     def _bits(self, planes=None):
         return self.sim.unpack(planes)[0].cpu().numpy()

@@ -9,6 +9,7 @@ bit-packed device state.  The host objects below keep the reference's attribute 
 import random
 
 import numpy as np
+import torch
 
 from gym_PBN.b200 import compiler, engine
 
@@ -115,6 +116,7 @@ class Graph:
         self.sim = engine.Simulator(self.network, 1, seed=0 if self._seed is None else self._seed)
         for n in self.nodes:
             n._graph = self
+        self._ids = [n.ID for n in self.nodes]
 
     @property
     def N(self):
@@ -129,16 +131,21 @@ class Graph:
         bits[i] = v
         self.sim.set_state(bits.reshape(1, -1))
 
-    def getState(self):
-        st = StateView(int(b) for b in self._bits())
-        st.ids = [n.ID for n in self.nodes]
+    def state_view(self, bits):
+        st = StateView(int(b) for b in bits)
+        st.ids = self._ids
         return st
+
+    def getState(self):
+        return self.state_view(self._bits())
 
     def getLabeledState(self):
         return dict(zip((n.ID for n in self.nodes), (int(b) for b in self._bits())))
 
     def setState(self, state):
-        self.sim.set_state(np.array([int(v) for v in state], dtype=np.uint8).reshape(1, self.N))
+        bits = np.array([int(v) for v in state], dtype=np.uint8)
+        words = np.packbits(np.pad(bits, (0, 32 * self.network.w32 - self.N)), bitorder="little").view(np.int32)
+        self.sim.state.copy_(torch.from_numpy(words.copy()).view(-1, 1))  # packed on the host: one small H2D copy
 
     def genRandState(self):
         """randint(0, base-1) per node from Python's `random`, as base.py:368-370."""

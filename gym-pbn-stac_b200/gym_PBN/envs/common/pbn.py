@@ -7,6 +7,7 @@
 it is O(2^N), constructor-time only, and feeds attractor lists, not the step path.
 """
 import numpy as np
+import torch
 
 from gym_PBN.b200 import compiler, engine
 from gym_PBN.utils import booleanize
@@ -46,7 +47,9 @@ class PBN:
 
     @state.setter
     def state(self, value):
-        self.sim.set_state(np.asarray(value, dtype=np.uint8).reshape(1, self.N))
+        bits = np.asarray(value, dtype=np.uint8).reshape(self.N) != 0
+        words = np.packbits(np.pad(bits, (0, 32 * self.network.w32 - self.N)), bitorder="little").view(np.int32)
+        self.sim.state.copy_(torch.from_numpy(words.copy()).view(-1, 1))  # packed on the host: one small H2D copy
 
     def reset(self, state=None):
         """Set the state (random when None); node 0 is forced to 0 exactly as common/pbn.py:77 does."""

@@ -45,5 +45,5 @@ class PBCNEnv(PBNEnv):
         if not 0 <= a < self.PBN.N:
             raise Exception(f"Invalid action {action}, not in action space.")
         reward, terminated, truncated, _ = self._run_step(self._env_image(), [a])
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         return observation, reward, terminated, truncated, {"observation_idx": state_to_idx(observation)}

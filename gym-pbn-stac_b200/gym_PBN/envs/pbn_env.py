@@ -98,7 +98,7 @@ class PBNEnv(DeviceEnvMixin, Env):
         if not self.action_space.contains(action):
             raise Exception(f"Invalid action {action}, not in action space.")
         reward, terminated, truncated, _ = self._run_step(self._env_image(), [int(action)])
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         return observation, reward, terminated, truncated, {"observation_idx": state_to_idx(observation)}
 
     def reset(self, seed=None, options=None):

@@ -138,10 +138,10 @@ class PBNTargetEnv(DeviceEnvMixin, Env):
         self.sim.target_att[0] = self._target_index
         reward, terminated, truncated, inner = self._run_step(self._env_image(force), [action])
         self.last_inner_steps = inner
-        observation = self.graph.getState()
+        observation = self.graph.state_view(self._last_state)
         info = {"observation_idx": state_to_idx(observation), "observation_dict": observation,
                 "inner_steps": inner, "inner_cap_hit": inner >= self.max_inner_steps}
-        return self.get_state(), reward, terminated, truncated, info
+        return self._last_state.astype(np.int64), reward, terminated, truncated, info
 
     def reset(self, seed=None, options=None):
         if seed:
@@ -158,7 +158,7 @@ class PBNTargetEnv(DeviceEnvMixin, Env):
                 target[i] = random.randint(0, 1)
         self.graph.setState(state)
         self.n_steps = 0
-        observation = self.graph.getState()
+        observation = self.graph.state_view(state)
         info = {"observation_idx": state_to_idx(observation), "observation_dict": observation}
         self.target = target_attractor
         self._target_index = self._index_of(target_attractor)

@@ -76,7 +76,7 @@ class PBNTargetMultiEnv(PBNTargetEnv):
         acts = [int(a) for a in actions] if len(actions) else [-1]
         reward, terminated, truncated, inner = self._run_step(image, acts)
         self.last_inner_steps = inner
-        observation = tuple(int(b) for b in self._bits(self.sim.obs_state))
+        observation = tuple(int(b) for b in self._last_obs)
         info = {"observation_idx": state_to_idx(observation), "observation_dict": observation,
                 "inner_steps": inner, "inner_cap_hit": inner >= self.max_inner_steps}
         return observation, reward, terminated, truncated, info
@@ -104,7 +104,7 @@ class PBNTargetMultiEnv(PBNTargetEnv):
                 target[i] = random.randint(0, 1)
         self.graph.setState(state)
         self.n_steps = 0
-        observation = self.graph.getState()
+        observation = self.graph.state_view(state)
         info = {"observation_idx": state_to_idx(observation), "observation_dict": observation}
         self.target = target_attractor
         self._target_index = self._index_of(target_attractor)

@@ -32,7 +32,7 @@ class PBNSampledDataEnv(PBNEnv):
             raise Exception(f"Invalid action {action}, not in action space.")
         control_action, interval = int(action[0]), int(action[1])
         reward, terminated, truncated, _ = self._run_step(self._env_image(), [control_action, interval])
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         info = {"control_action": control_action, "interval": interval - 1,  # the reference reports the last loop index
                 "observation_idx": state_to_idx(observation)}
         return observation, reward, terminated, truncated, info
@@ -72,6 +72,6 @@ class PBCNSampledDataEnv(PBCNEnv):
         control = [int(bool(c)) for c in np.asarray(control_action).reshape(-1)]
         self.PBN.apply_control(control)
         reward, terminated, truncated, _ = self._run_step(self._env_image(), [int(interval)] + control)
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         info = {"control_action": control_action, "interval": int(interval), "observation_idx": state_to_idx(observation)}
         return observation, reward, terminated, truncated, info

@@ -44,7 +44,7 @@ class PBNSelfTriggeringEnv(PBNEnv):
             total_reward += (self.gamma**i) * reward
             i += 1
             end = random.uniform(0, 1) <= prob or i == self.T
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         return observation, total_reward, terminated, truncated, {
             "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}
 
@@ -99,6 +99,6 @@ class PBCNSelfTriggeringEnv(PBCNEnv):
             total_reward += (self.gamma**i) * reward
             i += 1
             end = random.uniform(0, 1) <= prob or i == self.T
-        observation = self.PBN.state
+        observation = self._last_state.astype(bool)
         return observation, total_reward, terminated, truncated, {
             "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}

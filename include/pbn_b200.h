@@ -162,6 +162,19 @@ int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t e
 int pbn_unpack_state(const uint32_t *state, int64_t B, int32_t n_nodes, uint8_t *out, void *stream);
 int pbn_pack_state(const uint8_t *in, int64_t B, int32_t n_nodes, uint32_t *state, void *stream);
 
+/* Small-transfer helpers for the single-env drop-in classes (one env.step = one launch + one read-back):
+   pbn_upload enqueues a host->device copy on `stream`; pbn_fetch_host enqueues n device->host copies into one host
+   buffer (concatenated in order) and waits for the stream — the reference hands back host values (NumPy arrays, ints,
+   bools: pbn_env.py:150-154), so a synchronisation per step is part of its contract. */
+int pbn_upload(void *dst_dev, const void *src_host, int64_t nbytes, void *stream);
+int pbn_fetch_host(const void *const *src_dev, const int64_t *nbytes, int32_t n, void *dst_host, void *stream);
+/* Read-back of ONE env's step result (env index e of a batch of B): packs {reward int32, inner int32, terminated u8,
+   truncated u8, pad u16, state words [W32], obs words [W32]} into `scratch_dev` (>= 12 + 8*W32 bytes) with a 1-block
+   kernel, copies it to dst_host in a single transfer and waits for the stream. */
+int pbn_fetch_step_host(const int32_t *reward, const uint8_t *terminated, const uint8_t *truncated, const int32_t *inner,
+                        const uint32_t *state, const uint32_t *obs_state, int32_t w32, int64_t B, int64_t e,
+                        void *scratch_dev, void *dst_host, void *stream);
+
 /* instruction-issue microbenchmarks used by bench.py for the roofline denominator:
    kind 0 = dependent-free LOP3/IADD3 chain, kind 1 = Philox4x32-10 blocks.  Writes elapsed ms and the number of
    thread-level operations executed. */
