@@ -466,8 +466,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
     long long e = 0, nxt = lo + threadIdx.x;
     int in = 0, pend = 0;
     for (;;) {
-        if (!have) {
-            if (nxt >= hi) break;
+        if (!have && nxt < hi) {
             e = nxt;
             load_state(st, state, B, e, w32);
             d.init(dv, e, env0 + e);
@@ -496,34 +495,40 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
             in = 1;
             have = true;
         }
-        // while not force and not is_attracting_state(state): graph.step()                  (pbn_target.py:270-271)
-        // while not is_attracting_state(observation): observation = graph.step()            (pbn_target_multi.py:135-146)
-        const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting(ev, att_off, cubes, multi ? ob : st, w32);
-        if (!done) {
-            micro_step<NET, MODE>(nv, blob, st, d);
-            if (multi)
-                for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
-            in++;
-        } else {
-            int rew, tm = 0;
-            const int ta = target_att[e];
-            if (!multi) {  // PBNTargetEnv._get_reward, pbn_target.py:303-326: any cube of the target attractor
-                if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
-            } else {  // in_target returns at the first mismatch of the FIRST cube (Q12), pbn_target_multi.py:190-225
-                rew = pend;
-                if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew += 1000; tm = 1; }
+        // warp-uniform exit.  The full-mask vote is also where the lanes of the warp RE-CONVERGE every trip: without it,
+        // lanes that once took the finalize branch keep running as separate sub-warps (ncu: 2.9 active threads per
+        // instruction), because a loop with per-lane exits only reconverges at its end.
+        if (!__any_sync(0xFFFFFFFFu, have)) break;
+        if (have) {
+            // while not force and not is_attracting_state(state): graph.step()                  (pbn_target.py:270-271)
+            // while not is_attracting_state(observation): observation = graph.step()            (pbn_target_multi.py:135-146)
+            const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting(ev, att_off, cubes, multi ? ob : st, w32);
+            if (!done) {
+                micro_step<NET, MODE>(nv, blob, st, d);
+                if (multi)
+                    for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
+                in++;
+            } else {
+                int rew, tm = 0;
+                const int ta = target_att[e];
+                if (!multi) {  // PBNTargetEnv._get_reward, pbn_target.py:303-326: any cube of the target attractor
+                    if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
+                } else {  // in_target returns at the first mismatch of the FIRST cube (Q12), pbn_target_multi.py:190-225
+                    rew = pend;
+                    if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew += 1000; tm = 1; }
+                }
+                store_state(st, state, B, e, w32);
+                if (obs_state) store_state(multi ? ob : st, obs_state, B, e, w32);
+                reward[e] = rew;
+                terminated[e] = (unsigned char)tm;
+                const int tr = (n_steps[e] == ev.horizon);
+                truncated[e] = (unsigned char)tr;
+                if (inner_steps) inner_steps[e] = in;
+                d.done(dv, e);
+                if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, const_cast<int *>(target_att), obs_state, B, e, env0, rew, tm, tr, in);
+                have = false;
+                nxt = lo + atomicAdd(&s_next, 1);
             }
-            store_state(st, state, B, e, w32);
-            if (obs_state) store_state(multi ? ob : st, obs_state, B, e, w32);
-            reward[e] = rew;
-            terminated[e] = (unsigned char)tm;
-            const int tr = (n_steps[e] == ev.horizon);
-            truncated[e] = (unsigned char)tr;
-            if (inner_steps) inner_steps[e] = in;
-            d.done(dv, e);
-            if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, const_cast<int *>(target_att), obs_state, B, e, env0, rew, tm, tr, in);
-            have = false;
-            nxt = lo + atomicAdd(&s_next, 1);
         }
     }
     vec_flush_stats(vx, s_stats);
