@@ -360,7 +360,7 @@ def gen_target_env(ns, name="28_15_median", E=3, steps=250, horizon=20, cap=64, 
         out.update(tr.dump(f"e{e}/"))
         out[f"e{e}/force"] = int(force)
     print("target env micro-steps recorded:", inner_total)
-    np.savez_compressed(GOLD / "b28_target_env.npz", **out)
+    np.savez_compressed(GOLD / f"b{name.split('_')[0]}_target_env.npz", **out)
 
 
 def gen_multi_env(ns, name="28_15_median", E=2, steps=200, horizon=25, cap=64, seed=31):
@@ -391,7 +391,7 @@ def gen_multi_env(ns, name="28_15_median", E=2, steps=200, horizon=25, cap=64, s
                     tr.add(1, 0, rec.take(), st, tatt=len(atts) - 1)
         out.update(tr.dump(f"e{e}/"))
         out[f"e{e}/dedup"] = int(tensor_actions)
-    np.savez_compressed(GOLD / "b28_multi_env.npz", **out)
+    np.savez_compressed(GOLD / f"b{name.split('_')[0]}_multi_env.npz", **out)
 
 
 # ------------------------------------------------------------------------------------------ SSD
@@ -467,6 +467,8 @@ def main():
         "g200": lambda: gen_graph_core(ns, "200_5_kmeans", E=1, steps=300, sync_steps=5, seed=9),
         "target": lambda: gen_target_env(ns),
         "multi": lambda: gen_multi_env(ns),
+        "target100": lambda: gen_target_env(ns, name="100_5_kmeans", E=2, steps=120, horizon=15, cap=48, seed=51),
+        "multi100": lambda: gen_multi_env(ns, name="100_5_kmeans", E=2, steps=100, horizon=15, cap=48, seed=61),
         "ssd": lambda: gen_ssd_replay(ns),
     }
     for k, fn in jobs.items():

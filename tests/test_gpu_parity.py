@@ -142,8 +142,9 @@ def test_golden_pbcn_and_sampled_data(eng):
         _run_env_trace(eng, net, env, Traj(z, e), 1 if e == 0 else 2)
 
 
-def test_golden_target_env(eng):
-    z = load("b28_target_env.npz")
+@pytest.mark.parametrize("fname", ["b28_target_env.npz", "b100_target_env.npz"])
+def test_golden_target_env(eng, fname):
+    z = load(fname)
     net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
     atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
     for e in range(int(z["n_traj"])):
@@ -152,8 +153,9 @@ def test_golden_target_env(eng):
         _run_env_trace(eng, net, env, Traj(z, e), 1)
 
 
-def test_golden_multi_env(eng):
-    z = load("b28_multi_env.npz")
+@pytest.mark.parametrize("fname", ["b28_multi_env.npz", "b100_multi_env.npz"])
+def test_golden_multi_env(eng, fname):
+    z = load(fname)
     net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
     atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
     for e in range(int(z["n_traj"])):

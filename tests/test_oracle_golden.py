@@ -110,8 +110,9 @@ def test_pbcn_and_sampled_data_ex5():
         _run_env_trace(net, env, Traj(z, e), 1 if e == 0 else 2)
 
 
-def test_target_env_b28():
-    z = load("b28_target_env.npz")
+@pytest.mark.parametrize("fname", ["b28_target_env.npz", "b100_target_env.npz"])
+def test_target_env(fname):
+    z = load(fname)
     sets, ids = orc.load_bittner(str(z["pickle"]))
     net = orc.net_from_predictor_sets(sets, ids)
     atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
@@ -121,8 +122,9 @@ def test_target_env_b28():
         _run_env_trace(net, env, Traj(z, e), 1)
 
 
-def test_multi_env_b28():
-    z = load("b28_multi_env.npz")
+@pytest.mark.parametrize("fname", ["b28_multi_env.npz", "b100_multi_env.npz"])
+def test_multi_env(fname):
+    z = load(fname)
     sets, ids = orc.load_bittner(str(z["pickle"]))
     net = orc.net_from_predictor_sets(sets, ids)
     atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
