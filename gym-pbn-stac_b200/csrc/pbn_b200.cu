@@ -996,6 +996,47 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     return PBN_OK;
 }
 
+struct HistParams { int g; short tgt[24]; };
+__global__ void __launch_bounds__(256) k_bucket_hist(const u32 *state, long long B, HistParams hp, unsigned long long *hist) {
+    extern __shared__ u32 sh[];
+    const int nb = 1 << hp.g;
+    const bool smem = hp.g <= 12;
+    if (smem)
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < B; e += (long long)gridDim.x * blockDim.x) {
+        int b = 0;
+#pragma unroll
+        for (int k = 0; k < 24; k++)
+            if (k < hp.g) b = (b << 1) | (int)((state[(long long)(hp.tgt[k] >> 5) * B + e] >> (hp.tgt[k] & 31)) & 1u);
+        if (smem) atomicAdd(&sh[b], 1u);
+        else atomicAdd(&hist[b], 1ULL);
+    }
+    if (smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+            if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+    }
+}
+extern "C" int pbn_bucket_hist(const uint32_t *state, int64_t B, int32_t n_nodes, const int32_t *tgt, int32_t g, uint64_t *hist,
+                               void *stream) {
+    if (!state || !tgt || !hist || B < 0 || n_nodes < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if (g < 1 || g > 24) return fail(PBN_ERR_ARG, "1 <= g <= 24 target nodes");
+    if (B == 0) return PBN_OK;
+    HistParams hp;
+    memset(&hp, 0, sizeof hp);
+    hp.g = g;
+    for (int k = 0; k < g; k++) {
+        if (tgt[k] < 0 || tgt[k] >= n_nodes) return fail(PBN_ERR_ARG, "target node out of range");
+        hp.tgt[k] = (short)tgt[k];
+    }
+    long long blocks = (B + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_bucket_hist<<<(unsigned)blocks, 256, g <= 12 ? ((size_t)4 << g) : 0, (cudaStream_t)stream>>>(state, B, hp, (unsigned long long *)hist);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
 extern "C" int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t env0, int64_t iters, double p,
                             const int32_t *tgt, int32_t g, uint64_t seed, uint32_t epoch, uint64_t *hist_host) {
     if (!net || !hist_host || chains < 1) return fail(PBN_ERR_ARG, "bad argument");

@@ -224,6 +224,15 @@ class Simulator:
         return hist
 
 
+def bucket_hist(sim: "Simulator", tgt_nodes, hist):
+    """hist[bucket(state_e)] += 1 for every env of `sim` (target-node bits, first node most significant)."""
+    tgt = np.ascontiguousarray(tgt_nodes, np.int32)
+    with torch.cuda.device(sim.device):
+        abi.check(abi.lib().pbn_bucket_hist(_ptr(sim.state), sim.B, sim.net.n, _np_ptr(tgt), len(tgt), _ptr(hist), _stream()))
+        sim.launches += 1
+    return hist
+
+
 def issue_peak(kind, iters=2000):
     """(ops/s) of the instruction-issue microbenchmarks: kind 0 = INT ALU ops, kind 1 = Philox4x32-10 blocks."""
     ms, ops = C.c_float(), C.c_double()

@@ -68,6 +68,45 @@ def ssd_histogram(env, iters, chains, bit_flip_prob=0.01, seed=None, distributed
     return hist, per_chain * chains
 
 
+def _policy_actions(model, obs):
+    """Batched actions for uint8 observations [B][N] on the device.  A model with `predict_batch(obs)` is called once on
+    the device tensor; otherwise the reference protocol `model.predict(state, target, deterministic=True)` (target = state,
+    utils/eval.py:81-82,98) is called per chain on host arrays."""
+    if hasattr(model, "predict_batch"):
+        a = model.predict_batch(obs)
+        return torch.as_tensor(a).to(obs.device, dtype=torch.int32).reshape(obs.shape[0], -1)
+    host = obs.cpu().numpy()
+    acts = []
+    for row in host:
+        a = model.predict(row, row, deterministic=True)
+        if type(a) == tuple:
+            a = a[0]
+        acts.append(np.asarray(a).reshape(-1))
+    return torch.as_tensor(np.stack(acts).astype(np.int32)).to(obs.device)
+
+
+def ssd_histogram_policy(env, model, iters, chains, seed=None, distributed=True):
+    """The `model` branch of _ssd_run (utils/eval.py:97-101): per iteration  histogram -> action = model.predict(state)
+    -> env.step(action), no perturbation, no reset inside a chain.  All chains advance in lockstep through the fused
+    vector step; the histogram update is its own small kernel (pbn_bucket_hist)."""
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    start, stop = pdist.shard_range(chains) if distributed else (0, chains)
+    seed = env._next_seed() if seed is None else seed
+    tgt = np.asarray(env.target_node_indices, np.int32)
+    hist = torch.zeros(1 << len(tgt), dtype=torch.int64, device=env.network.device)
+    if stop > start:
+        vec = PBNVectorEnv(env, stop - start, seed=seed, autoreset=False)
+        vec.sim.env0 = start
+        obs, _ = vec.reset()
+        for _ in range(int(iters)):
+            engine.bucket_hist(vec.sim, tgt, hist)
+            obs, *_ = vec.step(_policy_actions(model, obs))
+    if distributed:
+        pdist.allreduce_sum_(hist)
+    return hist, int(iters) * chains
+
+
 def compute_ssd_hist(env, model=None, iters=1_200_000, resets=300, bit_flip_prob=0.01, multiprocess=True, seed=None):
     """Reference signature (utils/eval.py:20-27).  Returns (DataFrame indexed '0..0'..'1..1' MSB-first with column
     "Value", figure-or-None).  `multiprocess` is accepted for compatibility; parallelism here is the GPU's."""
@@ -76,10 +115,11 @@ def compute_ssd_hist(env, model=None, iters=1_200_000, resets=300, bit_flip_prob
     assert SSD_RESETS > 0, "Invalid resets value."
     assert SSD_N > 0, "Invalid iterations value."
     assert SSD_N // SSD_RESETS, "Resets does not divide the iterations."
-    if model is not None:
-        raise NotImplementedError("policy-in-the-loop SSD (model.predict per step) is not on the GPU path yet")
     g = len(env.target_nodes)
-    hist, total = ssd_histogram(env, SSD_N // SSD_RESETS, SSD_RESETS, bit_flip_prob, seed=seed)
+    if model is not None:
+        hist, total = ssd_histogram_policy(env, model, SSD_N // SSD_RESETS, SSD_RESETS, seed=seed)
+    else:
+        hist, total = ssd_histogram(env, SSD_N // SSD_RESETS, SSD_RESETS, bit_flip_prob, seed=seed)
     ssd = hist.cpu().numpy().astype(np.float64) / float(total)
     states = ["".join(str(b) for b in bits) for bits in itertools.product([0, 1], repeat=g)]
     try:

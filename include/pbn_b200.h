@@ -152,6 +152,11 @@ int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chain
             double bit_flip_prob, const int32_t *tgt_nodes_host, int32_t g, uint64_t *hist, const PbnDraws *draws,
             void *stream);
 
+/* hist[bucket(state_e)] += 1 for every env e — the first two lines of an _ssd_run iteration (utils/eval.py:88-89) as a
+   stand-alone kernel, for estimates whose actions come from a policy between steps (eval.py:97-101). */
+int pbn_bucket_hist(const uint32_t *state, int64_t B, int32_t n_nodes, const int32_t *tgt_nodes_host, int32_t g,
+                    uint64_t *hist, void *stream);
+
 /* Same estimate with HOST buffers: uploads nothing but the description, draws random start states on device
    (genRandState), runs K3 and copies the histogram back; blocks until done.  The call compute_ssd_hist maps to. */
 int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t env0, int64_t iters,

@@ -434,6 +434,55 @@ def gen_ssd_replay(ns, name="100_5_kmeans", chains=2, iters=150, seed=41):
     np.savez_compressed(GOLD / "b100_ssd_replay.npz", **out)
 
 
+class GoldenPolicy:
+    """Deterministic stand-in for an agent: flip the first target gene that is 0 (1-indexed action), else no action."""
+
+    def __init__(self, tgt_idx):
+        self.tgt_idx = list(tgt_idx)
+
+    def predict(self, state, target, deterministic=True):
+        for i in self.tgt_idx:
+            if int(state[i]) == 0:
+                return (i + 1, None)
+        return (0, None)
+
+
+def gen_ssd_policy(ns, name="28_15_median", iters=250, horizon=10**9, cap=64, seed=71):
+    """The `model` branch of _ssd_run (utils/eval.py:97-101) on Bittner-28 with the attractor fixture."""
+    sets, ids = load_sets(name)
+    n = len(ids)
+    atts = fixture_attractors(ns, name)
+    cubes, off = cubes_to_arrays(atts, n)
+    env = bind_env(ns, ns.pbn_target.PBNTargetEnv, sets, ids, atts, horizon, cap)
+    env.target_nodes = ids[:5]
+    tgt_idx = list(range(5))
+    random.seed(seed), np.random.seed(seed)
+    int_off, dbl_off, ints, dbls, actions = [0], [0], [], [], []
+    with ref_loader.Recorder() as rec, quiet():
+        env.reset()
+        rec.take()
+        init = np.array(env.graph.getState(), np.uint8)
+        tatt = atts.index(env.target)
+        orig_step = env.step
+
+        def step(action=0, force=False):
+            env._calls["n"] = 0
+            out = orig_step(action, force)
+            i, d = rec.take()
+            ints.extend(i), dbls.extend(d)
+            int_off.append(len(ints)), dbl_off.append(len(dbls)), actions.append(int(action))
+            return out
+
+        env.step = step
+        env.reset = lambda *a, **k: None
+        h = ns.eval._ssd_run(5, iters, 0.01, GoldenPolicy(tgt_idx), env)
+    np.savez_compressed(GOLD / "b28_ssd_policy.npz", pickle=np.array(name), att_cubes=cubes, att_off=off, cap=cap,
+                        init=init, target_att=tatt, hist=h.astype(np.int64), tgt_nodes=np.array(tgt_idx, np.int32),
+                        actions=np.array(actions, np.int32), ints=np.array(ints, np.int32), dbls=np.array(dbls, np.float64),
+                        int_off=np.array(int_off, np.int64), dbl_off=np.array(dbl_off, np.int64),
+                        final=np.array(env.graph.getState(), np.uint8))
+
+
 def gen_ssd_long(ns, name="100_5_kmeans", iters=1_200_000, resets=300):
     """Two independent full-size reference estimates (utils/eval.py:20-72 defaults) — the TV yardstick."""
     import pandas as pd  # noqa: F401
@@ -470,6 +519,7 @@ def main():
         "target100": lambda: gen_target_env(ns, name="100_5_kmeans", E=2, steps=120, horizon=15, cap=48, seed=51),
         "multi100": lambda: gen_multi_env(ns, name="100_5_kmeans", E=2, steps=100, horizon=15, cap=48, seed=61),
         "ssd": lambda: gen_ssd_replay(ns),
+        "ssd_policy": lambda: gen_ssd_policy(ns),
     }
     for k, fn in jobs.items():
         if args.only in (None, k):

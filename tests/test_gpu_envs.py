@@ -287,3 +287,35 @@ def test_abi_error_paths():
         spec = compiler.load_bittner("28_15_median")
         spec.n = 300
         engine.Network(spec)
+
+
+def test_compute_ssd_hist_with_model():
+    """compute_ssd_hist(env, model=...) — the policy branch of the reference (utils/eval.py:97-101) on the GPU path."""
+    import gym_PBN
+    from gym_PBN.utils.eval import compute_ssd_hist
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=64).unwrapped
+    tgt_idx = env.target_node_indices
+
+    class RefStyle:  # the reference protocol: predict(state, target, deterministic) -> (action, _)
+        def predict(self, state, target, deterministic=True):
+            for i in tgt_idx:
+                if int(state[i]) == 0:
+                    return (i + 1, None)
+            return (0, None)
+
+    class Batched:  # device-side protocol
+        def predict_batch(self, obs):
+            sub = obs[:, tgt_idx]
+            zero = (sub == 0)
+            first = torch.argmax(zero.to(torch.int32), dim=1)
+            idx = torch.tensor(tgt_idx, device=obs.device)[first] + 1
+            return torch.where(zero.any(1), idx, torch.zeros_like(idx)).to(torch.int32)
+
+    a, _ = compute_ssd_hist(env, model=RefStyle(), iters=64 * 40, resets=64, seed=5)
+    b, _ = compute_ssd_hist(env, model=Batched(), iters=64 * 40, resets=64, seed=5)
+    va, vb = np.asarray(a["Value"]), np.asarray(b["Value"])
+    assert abs(va.sum() - 1.0) < 1e-12 and np.array_equal(va, vb)
+    assert va[-1] > 0.3  # the policy drives the target genes to all-ones

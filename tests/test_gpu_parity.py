@@ -448,3 +448,34 @@ def test_ssd_split_invariance(eng):
     bad = eng.engine.Simulator(net, 64, seed=4, env0=5)
     with pytest.raises(ValueError):
         bad.ssd(10, 0.02, tgt)
+
+
+def test_golden_ssd_policy_branch(eng):
+    """The `model` branch of _ssd_run replayed through the C-ABI: pbn_bucket_hist + pbn_env_step per iteration."""
+    z = load("b28_ssd_policy.npz")
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = eng.engine.EnvImage(net, eng.abi.ENV_TARGET, attractors=atts, horizon=10**9, max_inner=int(z["cap"]))
+    sim = eng.engine.Simulator(net, 1)
+    sim.set_state(z["init"].reshape(1, -1))
+    sim.target_att[0] = int(z["target_att"])
+    tgt = z["tgt_nodes"]
+    hist = torch.zeros(1 << len(tgt), dtype=torch.int64, device="cuda")
+    for t, a in enumerate(z["actions"]):
+        eng.engine.bucket_hist(sim, tgt, hist)
+        rp = _replay(eng, z["ints"][z["int_off"][t]:z["int_off"][t + 1]], z["dbls"][z["dbl_off"][t]:z["dbl_off"][t + 1]])
+        sim.env_step(env, torch.tensor([[int(a)]], dtype=torch.int32), replay=rp)
+    assert np.array_equal(hist.cpu().numpy(), z["hist"])
+    assert np.array_equal(_state_np(sim)[0], z["final"])
+
+
+def test_bucket_hist_large_batch(eng):
+    net, _ = _nets(eng, "100_5_kmeans")
+    sim = eng.engine.Simulator(net, 100_000, seed=2)
+    sim.rand_state()
+    for tgt in (np.array([0, 1, 2, 3, 4, 5, 6], np.int32), np.array([99, 3, 64, 31, 32], np.int32), np.arange(14, dtype=np.int32)):
+        hist = torch.zeros(1 << len(tgt), dtype=torch.int64, device="cuda")
+        eng.engine.bucket_hist(sim, tgt, hist)
+        bits = _state_np(sim)[:, tgt].astype(np.int64)
+        idx = (bits * (1 << np.arange(len(tgt) - 1, -1, -1))).sum(1)
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(idx, minlength=1 << len(tgt)))

@@ -144,3 +144,24 @@ def test_ssd_replay_b100():
     hist = orc.ssd(net, env, st, int(z["iters"]), float(z["p"]), z["tgt_nodes"], d)
     assert np.array_equal(hist.astype(np.int64), z["hist"].sum(0))
     assert np.array_equal(d.used[:, 0], [z["ints"].shape[1]] * 2) and np.array_equal(d.used[:, 1], [z["dbls"].shape[1]] * 2)
+
+
+def test_ssd_policy_branch_b28():
+    """The `model` branch of _ssd_run (utils/eval.py:97-101): histogram -> model.predict -> env.step(action)."""
+    z = load("b28_ssd_policy.npz")
+    sets, ids = orc.load_bittner(str(z["pickle"]))
+    net = orc.net_from_predictor_sets(sets, ids)
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = orc.Env(orc.ENV_TARGET, net.n, attractors=atts, horizon=10**9, max_inner=int(z["cap"]))
+    st = z["init"].reshape(1, -1).copy()
+    n_steps, tatt = np.zeros(1, np.int32), np.array([int(z["target_att"])], np.int32)
+    tgt = z["tgt_nodes"]
+    hist = np.zeros(1 << len(tgt), np.int64)
+    for t, a in enumerate(z["actions"]):
+        hist[int("".join(str(int(st[0, i])) for i in tgt), 2)] += 1
+        # the policy's decision is a function of the state: first target gene that is 0
+        zeros = [i for i in tgt if st[0, i] == 0]
+        assert a == (zeros[0] + 1 if zeros else 0)
+        d = _rd(z["ints"][z["int_off"][t]:z["int_off"][t + 1]], z["dbls"][z["dbl_off"][t]:z["dbl_off"][t + 1]])
+        orc.env_step(net, env, st, n_steps, tatt, np.array([[a]], np.int32), d)
+    assert np.array_equal(hist, z["hist"]) and np.array_equal(st[0], z["final"])
