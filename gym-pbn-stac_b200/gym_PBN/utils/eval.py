@@ -131,6 +131,19 @@ def compute_ssd_hist(env, model=None, iters=1_200_000, resets=300, bit_flip_prob
     return ret, visualize_ssd(ret, getattr(env, "name", None))
 
 
+def eval_increase(env, model, original_ssd=None, iters=1_200_000, resets=300, bit_flip_prob=0.01):
+    """Total increase of the favourable target-gene patterns (env.target_node_values) in the SSD under `model` versus the
+    uncontrolled SSD (reference: utils/eval.py:106-136; there the subtraction is applied to the (frame, figure) tuples
+    that compute_ssd_hist returns and cannot run — here it is applied to the frames)."""
+    if original_ssd is None:
+        original_ssd = compute_ssd_hist(env, iters=iters, resets=resets, bit_flip_prob=bit_flip_prob)
+    model_ssd = compute_ssd_hist(env, model, iters=iters, resets=resets, bit_flip_prob=bit_flip_prob)
+    frame = lambda x: x[0] if isinstance(x, tuple) else x  # noqa: E731
+    states = ["".join(str(int(b)) for b in state) for state in env.target_node_values]
+    delta = frame(model_ssd) - frame(original_ssd)
+    return float(delta.loc[states, "Value"].sum())
+
+
 def visualize_ssd(ssd_frame, env_name):
     """Bar chart of the estimate when plotly is installed (reference: utils/eval.py:139-157); None otherwise."""
     try:

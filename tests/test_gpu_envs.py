@@ -319,3 +319,24 @@ def test_compute_ssd_hist_with_model():
     va, vb = np.asarray(a["Value"]), np.asarray(b["Value"])
     assert abs(va.sum() - 1.0) < 1e-12 and np.array_equal(va, vb)
     assert va[-1] > 0.3  # the policy drives the target genes to all-ones
+
+
+def test_eval_increase():
+    import gym_PBN
+    from gym_PBN.utils.eval import eval_increase
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=64).unwrapped
+    env.target_node_values = ((1, 1, 1, 1, 1, 1, 1),)
+    tgt_idx = env.target_node_indices
+
+    class Policy:
+        def predict_batch(self, obs):
+            zero = obs[:, tgt_idx] == 0
+            first = torch.argmax(zero.to(torch.int32), dim=1)
+            idx = torch.tensor(tgt_idx, device=obs.device)[first] + 1
+            return torch.where(zero.any(1), idx, torch.zeros_like(idx)).to(torch.int32)
+
+    inc = eval_increase(env, Policy(), iters=128 * 30, resets=128)
+    assert 0.0 < inc <= 1.0  # steering every target gene to 1 raises the mass of the all-ones pattern
