@@ -1,0 +1,1 @@
+"""Bittner melanoma predictor-graph networks (device-backed) and the shipped predictor sets."""

@@ -1,0 +1,1 @@
+"""Truth-table PBN / PBCN cores (device-backed)."""

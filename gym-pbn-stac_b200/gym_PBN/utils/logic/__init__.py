@@ -1,0 +1,1 @@
+"""Boolean expression compiler for logic_func_data."""
