@@ -1061,6 +1061,121 @@ extern "C" int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains
     return rc;
 }
 
+// ----------------------------------------------------------------------------------------------- exhaustive STG
+// masks[s] bit i = node i can change value in state s.  Reads the packed image straight from global memory (one pass
+// over 2^N states, not a hot loop); probabilities are compared as float64 exactly like common/pbn.py:186-197.
+__global__ void __launch_bounds__(256) k_change_masks(NetView nv, u32 *masks) {
+    const unsigned long long total = 1ULL << nv.n;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < total;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        const u32 st = (u32)s;
+        u32 m = 0;
+        if (nv.kind == PBN_NET_TT) {
+            const uint2 *node = reinterpret_cast<const uint2 *>(nv.blob + nv.off_node);
+            const unsigned short *in = reinterpret_cast<const unsigned short *>(nv.blob + nv.off_in);
+            for (int i = 0; i < nv.n; i++) {
+                const uint2 nr = node[i];
+                const int k = (int)(nr.y >> 16);
+                u32 idx = 0;
+                for (int q = 0; q < k; q++) idx = (idx << 1) | ((st >> in[(nr.y & 0xFFFF) + q]) & 1u);
+                const double p = nv.tt_prob[nr.x + idx];
+                const u32 cur = (st >> i) & 1u;
+                if ((cur == 0 && p > 0.0) || (cur == 1 && p < 1.0)) m |= 1u << i;
+            }
+        } else {
+            const uint2 *rec = reinterpret_cast<const uint2 *>(nv.blob + nv.off_rec);
+            for (int i = 0; i < nv.n; i++) {
+                const int q0 = nv.pr_off[i], f = nv.pr_off[i + 1] - q0;
+                const u32 cur = (st >> i) & 1u;
+                bool can = false;
+                double prev = 0.0;
+                for (int j = 0; j < f; j++) {
+                    const double c = nv.pr_cum[q0 + j];
+                    if (c > prev) {  // predictor j has positive COD weight: it can be drawn (base.py:94-97)
+                        const uint2 r = rec[i * nv.fmax + j];
+                        const u32 idx = (((st >> (r.x & 0xFF)) & 1u) << 3) | (((st >> ((r.x >> 8) & 0xFF)) & 1u) << 2) |
+                                        (((st >> ((r.x >> 16) & 0xFF)) & 1u) << 1) | ((st >> (r.x >> 24)) & 1u);
+                        can |= (((r.y >> idx) & 1u) != cur);
+                    }
+                    prev = c;
+                }
+                if (can) m |= 1u << i;
+            }
+        }
+        masks[s] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stg_expand(const u32 *masks, int n, const u32 *frontier, const u32 *visited,
+                                                    const u32 *within, u32 *next, int direction) {
+    const unsigned long long words = (1ULL << n) >> 5 ? (1ULL << n) >> 5 : 1ULL;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        u32 fw = frontier[w];
+        while (fw) {
+            const int b = __ffs(fw) - 1;
+            fw &= fw - 1;
+            const u32 s = (u32)(w << 5) | (u32)b;
+            if (direction == 0) {  // successors: s ^ (1<<i) for every changeable node i
+                u32 m = masks[s];
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u32 t = s ^ (1u << i), tw = t >> 5, tb = 1u << (t & 31);
+                    if (!(visited[tw] & tb) && (!within || (within[tw] & tb))) atomicOr(&next[tw], tb);
+                }
+            } else {  // predecessors: t = s ^ (1<<i) with node i changeable in t
+                for (int i = 0; i < n; i++) {
+                    const u32 t = s ^ (1u << i), tw = t >> 5, tb = 1u << (t & 31);
+                    if (!(visited[tw] & tb) && (!within || (within[tw] & tb)) && ((masks[t] >> i) & 1u)) atomicOr(&next[tw], tb);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_stg_walk(const u32 *masks, int n, u32 start, long long steps, u32 k0, u32 k1, u32 *out) {
+    u32 s = start, o0, o1, o2, o3;
+    for (long long t = 0; t < steps; t++) {
+        const u32 m = masks[s];
+        if (!m) break;  // fixed point
+        philox4x32_10((u32)t, (u32)(t >> 32), 0x57a1u, 0, k0, k1, o0, o1, o2, o3);
+        int pick = (int)__umulhi(o0, (u32)__popc(m));
+        u32 mm = m;
+        while (pick--) mm &= mm - 1;
+        s ^= 1u << (__ffs(mm) - 1);
+    }
+    *out = s;
+}
+
+extern "C" int pbn_stg_change_masks(const PbnNet *net, uint32_t *masks, void *stream) {
+    if (!net || !masks) return fail(PBN_ERR_ARG, "bad argument");
+    if (net->v.n > 32) return fail(PBN_ERR_UNSUPPORTED, "the exhaustive state-transition graph supports at most 32 nodes");
+    const unsigned long long total = 1ULL << net->v.n;
+    unsigned long long blocks = (total + 255) / 256;
+    if (blocks > 148ULL * 32) blocks = 148ULL * 32;
+    k_change_masks<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(net->v, masks);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+extern "C" int pbn_stg_expand(const uint32_t *masks, int32_t n, const uint32_t *frontier, const uint32_t *visited,
+                              const uint32_t *within, uint32_t *next, int32_t direction, void *stream) {
+    if (!masks || !frontier || !visited || !next || n < 1 || n > 32) return fail(PBN_ERR_ARG, "bad argument");
+    const unsigned long long words = ((1ULL << n) + 31) >> 5;
+    unsigned long long blocks = (words + 255) / 256;
+    if (blocks > 148ULL * 32) blocks = 148ULL * 32;
+    k_stg_expand<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(masks, n, frontier, visited, within, next, direction);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+extern "C" int pbn_stg_walk(const uint32_t *masks, int32_t n, uint32_t start, int64_t steps, uint64_t seed, uint32_t *out,
+                            void *stream) {
+    if (!masks || !out || n < 1 || n > 32 || steps < 0) return fail(PBN_ERR_ARG, "bad argument");
+    k_stg_walk<<<1, 1, 0, (cudaStream_t)stream>>>(masks, n, start, steps, (u32)seed, (u32)(seed >> 32), out);
+    CK(cudaGetLastError());
+    return PBN_OK;
+}
+
 extern "C" int pbn_upload(void *dst_dev, const void *src_host, int64_t nbytes, void *stream) {
     if (!dst_dev || !src_host || nbytes < 0) return fail(PBN_ERR_ARG, "bad argument");
     CK(cudaMemcpyAsync(dst_dev, src_host, (size_t)nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));

@@ -66,6 +66,9 @@ EXPORTS = {
                                C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "pbn_unpack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_pack_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pbn_stg_change_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbn_stg_expand": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pbn_stg_walk": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pbn_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pbn_fetch_host": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_fetch_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -127,9 +127,17 @@ class PBN:
             self.STG = G
         return self.STG
 
-    def attractors(self, max_nodes=22):
-        """Terminal strongly connected components of the asynchronous STG, as a list of sets of state tuples
-        (what PBNEnv.compute_attractors obtains from networkx, pbn_env.py:238-255).  Host-side and vectorised over all
+    def attractors(self, max_nodes=26):
+        """Attractors of the asynchronous STG (list of sets of state tuples, as PBNEnv.compute_attractors returns them,
+        pbn_env.py:238-255), computed on the device (gym_PBN.b200.attractors.exact_attractors)."""
+        from gym_PBN.b200 import attractors as _att
+
+        if self.N > max_nodes:
+            raise ValueError(f"exhaustive attractor search is O(2^N); N={self.N} > {max_nodes}")
+        return _att.attractor_state_sets(self.network, list_limit=1 << 22)
+
+    def attractors_host(self, max_nodes=22):
+        """Host-side reference of `attractors` (NumPy + SciPy strongly connected components), vectorised over all
         2^N states; edges follow common/pbn.py:186-197 (node i can change value: p > 0 from 0, p < 1 from 1)."""
         from scipy.sparse import csr_matrix
         from scipy.sparse.csgraph import connected_components

@@ -19,7 +19,7 @@ class PBNEnv(DeviceEnvMixin, Env):
     metadata = {"render_modes": ["human", "PBN", "STG", "funcs", "idx", "float"]}
     _CORE = PBN
     _KIND = abi.ENV_PBN
-    MAX_EXHAUSTIVE_NODES = 20
+    MAX_EXHAUSTIVE_NODES = 26  # the exhaustive STG lives on the device: 2^26 states x 4 B of change masks
 
     def __init__(self, render_mode="human", render_no_cache=False, PBN_data=None, logic_func_data=None, name=None,
                  goal_config=None, reward_config=None, device=None, seed=None, **core_kwargs):

@@ -64,6 +64,7 @@ class PBNTargetEnv(DeviceEnvMixin, Env):
         self._all_attractors = [list(a) for a in (all_attractors or [])]
         self._target_index = -1
         self.last_inner_steps = 0
+        self.attractor_source = "given" if self._all_attractors else None
 
     # ---- config / attractors ---------------------------------------------------------------------------------
     def _check_config(self, config, _type, required_keys, default_values=None):
@@ -220,9 +221,10 @@ class _BittnerTarget(PBNTargetEnv):
         PBNTargetEnv.__init__(self, graph, goal, render_mode, render_no_cache, name or self.NAME, reward_config,
                               end_episode_on_success, all_attractors=all_attractors, max_inner_steps=max_inner_steps)
         if not self._all_attractors:
-            # no CABEAN here: the reference's own sampling recipe, projected on the target genes
-            self.all_attractors = att_tools.statistical_attractors(self.network, resets=100, steps=1000, top=4,
-                                                                   care_nodes=self.target_node_indices, seed=seed or 0)
+            # no CABEAN here: exact terminal SCCs of the asynchronous STG (N <= 28), else the reference's own sampling
+            # recipe projected on the target genes
+            self.all_attractors, self.attractor_source = att_tools.default_attractors(
+                self.network, self.target_node_indices, seed=seed or 0)
 
 
 class Bittner70(_BittnerTarget):

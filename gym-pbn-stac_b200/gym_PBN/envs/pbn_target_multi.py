@@ -152,8 +152,8 @@ class _BittnerMulti(PBNTargetMultiEnv):
                          end_episode_on_success, all_attractors=all_attractors, max_inner_steps=max_inner_steps,
                          sample_pair=sample_pair)
         if not self._all_attractors:
-            self.all_attractors = att_tools.statistical_attractors(self.network, resets=100, steps=1000, top=4,
-                                                                   care_nodes=self.target_node_indices, seed=seed or 0)
+            self.all_attractors, self.attractor_source = att_tools.default_attractors(
+                self.network, self.target_node_indices, seed=seed or 0)
 
 
 class BittnerMulti7(_BittnerMulti):

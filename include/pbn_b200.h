@@ -167,6 +167,22 @@ int pbn_ssd_host(const PbnNet *net, const PbnEnv *env, int64_t chains, int64_t e
 int pbn_unpack_state(const uint32_t *state, int64_t B, int32_t n_nodes, uint8_t *out, void *stream);
 int pbn_pack_state(const uint8_t *in, int64_t B, int32_t n_nodes, uint32_t *state, void *stream);
 
+/* Exhaustive asynchronous state-transition graph on the device (networks up to 32 nodes; state s = bit i is node i).
+   Replaces the O(2^N) host loops behind PBNEnv.compute_attractors (pbn_env.py:238-244 -> PBN.print_STG /
+   _compute_next_states common/pbn.py:132-197) and Graph.genSTG / getNextStates / findAttractors
+   (bittner/base.py:199-242,398-399); the attractors are the terminal strongly connected components.
+     pbn_stg_change_masks  masks[s] bit i = node i can change value in state s (edge s -> s ^ (1<<i)):
+                           truth tables: P(next=1) > 0 from 0, < 1 from 1 (common/pbn.py:186-197, float64 tables);
+                           predictor graphs: some predictor with positive COD weight outputs the other value.
+     pbn_stg_expand        one BFS level over bitsets of 2^N bits: next |= neighbours(frontier) & ~visited (& within).
+                           direction 0 = successors, 1 = predecessors.  `within` may be NULL.
+     pbn_stg_walk          `steps` uniformly random forward moves from `start` (a cheap way to land in a terminal SCC). */
+int pbn_stg_change_masks(const PbnNet *net, uint32_t *masks, void *stream);
+int pbn_stg_expand(const uint32_t *masks, int32_t n_nodes, const uint32_t *frontier, const uint32_t *visited,
+                   const uint32_t *within, uint32_t *next, int32_t direction, void *stream);
+int pbn_stg_walk(const uint32_t *masks, int32_t n_nodes, uint32_t start, int64_t steps, uint64_t seed, uint32_t *out,
+                 void *stream);
+
 /* Small-transfer helpers for the single-env drop-in classes (one env.step = one launch + one read-back):
    pbn_upload enqueues a host->device copy on `stream`; pbn_fetch_host enqueues n device->host copies into one host
    buffer (concatenated in order) and waits for the stream — the reference hands back host values (NumPy arrays, ints,

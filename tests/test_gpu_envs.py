@@ -340,3 +340,83 @@ def test_eval_increase():
 
     inc = eval_increase(env, Policy(), iters=128 * 30, resets=128)
     assert 0.0 < inc <= 1.0  # steering every target gene to 1 raises the mass of the all-ones pattern
+
+
+def test_exact_attractors_on_gpu_match_host_and_reference():
+    """Terminal SCCs of the exhaustive async STG computed on the device == the host search == the reference's
+    compute_attractors (recorded for five random networks and the example network)."""
+    from gym_PBN.b200 import attractors, compiler, engine
+    from gym_PBN.envs.common.node import Node
+    from gym_PBN.envs.common.pbn import PBN
+
+    z = load("tt_attractors.npz")
+    for k in range(int(z["n_nets"])):
+        masks, tables = z[f"n{k}/masks"], z[f"n{k}/tables"]
+        n = len(masks)
+        data = [(masks[i], tables[i, : 2 ** int(masks[i].sum())], f"g{i}", False) for i in range(n)]
+        net = engine.Network(compiler.compile_pbn_data(data))
+        got = sorted(sorted(a) for a in attractors.attractor_state_sets(net))
+        states = [tuple(int(v) for v in s) for s in z[f"n{k}/att_states"]]
+        want, pos = [], 0
+        for sz in z[f"n{k}/att_sizes"]:
+            want.append(sorted(states[pos:pos + sz]))
+            pos += sz
+        assert got == sorted(want), k
+    # larger random networks against the host search
+    rng = np.random.default_rng(3)
+    for n in (11, 14, 16):
+        data = []
+        for i in range(n):
+            kin = int(rng.integers(1, 4))
+            mask = np.zeros(n, bool)
+            mask[rng.choice(n, size=kin, replace=False)] = True
+            table = rng.choice([0.0, 1.0, 1.0, 0.0, 0.4], size=2**kin)
+            data.append((mask, table, f"g{i}", False))
+        net = engine.Network(compiler.compile_pbn_data(data))
+        pbn = PBN.__new__(PBN)
+        pbn.N = n
+        pbn.nodes = np.empty(n, dtype=object)
+        for i, (m, t, *_r) in enumerate(data):
+            pbn.nodes[i] = Node(m, t, i)
+        host = sorted(sorted(a) for a in pbn.attractors_host())
+        dev = sorted(sorted(a) for a in attractors.attractor_state_sets(net, list_limit=1 << 20))
+        assert dev == host, n
+
+
+def test_exact_attractors_predictor_graph_28():
+    """The shipped 28-gene predictor graph: every reported attractor is closed under the dynamics (no change mask leads out)."""
+    from gym_PBN.b200 import attractors, compiler, engine
+
+    net = engine.Network(compiler.load_bittner("28_15_median"))
+    found = attractors.exact_attractors(net, list_limit=4096)
+    assert found and sum(a["size"] for a in found) >= 1
+    stg = attractors.StateTransitionGraph(net)
+    for a in found[:3]:
+        bits = a["bits"] if a["bits"] is not None else stg.single(int(a["states"][0]))
+        fwd = stg.reach(bits, 0)
+        assert torch.equal(fwd, bits)  # closed: nothing outside is reachable
+    print("Bittner-28 attractors:", [a["size"] for a in found][:10], "count", len(found))
+
+
+def test_bittner28_default_attractors_are_exact():
+    """gym.make("gym-PBN/Bittner-28-v0") without an attractor list: exact terminal SCCs of the async STG, as cubes."""
+    import gym_PBN
+    from gym_PBN.b200 import attractors
+
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", seed=3)
+    core = env.unwrapped
+    assert core.attractor_source == "exact" and len(core.all_attractors) >= 2
+    sizes = sorted(sum(2 ** sum(v == "*" for v in c) for c in a) for a in core.all_attractors)
+    found = attractors.exact_attractors(core.network, list_limit=1 << 17)
+    assert sizes == sorted(a["size"] for a in found)
+    small = min(found, key=lambda a: a["size"])
+    cubes = next(a for a in core.all_attractors if sum(2 ** sum(v == "*" for v in c) for c in a) == small["size"])
+    listed = {tuple((int(s) >> i) & 1 for i in range(28)) for s in small["states"]}
+    assert {t for c in cubes for t in attractors.expand_cube(c)} == listed
+    for t in list(listed)[:20]:
+        assert core.is_attracting_state(t)
+    (state, target), _ = env.reset(seed=3)
+    assert core.is_attracting_state(state)
+    for a in (0, 5, 0, 17, 0):
+        obs, r, term, trunc, info = env.step(a)
+        assert core.is_attracting_state(obs) or info["inner_cap_hit"]

@@ -195,7 +195,7 @@ def test_exhaustive_attractors_match_reference():
         for i in range(n):
             kin = int(masks[i].sum())
             pbn.nodes[i] = Node(masks[i], tables[i, : 2**kin], i)
-        got = sorted(sorted(a) for a in pbn.attractors())
+        got = sorted(sorted(a) for a in pbn.attractors_host())
         sizes = z[f"n{k}/att_sizes"]
         states = [tuple(int(v) for v in s) for s in z[f"n{k}/att_states"]]
         want, pos = [], 0
