@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 // contiguous range of envs and its threads pull the next env from a block-local counter the moment they finish one, in a
 // flat loop whose every trip is "one attractor test + at most one update" for every lane — lanes never wait at the end
 // of an inner loop.  An env's result does not depend on which thread ran it (its Philox stream is keyed by its id).
-template <int NET, int MODE>
+template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
                 pend = -cnt;  // reward -= len(actions)
                 for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
             }
-            micro_step<NET, MODE>(nv, blob, st, d);
+            micro_step<NET, MODE, TQ>(nv, blob, st, d);
             in = 1;
             have = true;
         }
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
             // while not is_attracting_state(observation): observation = graph.step()            (pbn_target_multi.py:135-146)
             const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting(ev, att_off, cubes, multi ? ob : st, w32);
             if (!done) {
-                micro_step<NET, MODE>(nv, blob, st, d);
+                micro_step<NET, MODE, TQ>(nv, blob, st, d);
                 if (multi)
                     for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
                 in++;
@@ -871,24 +871,24 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                                                          \
     if (att) {                                                                                                    \
-        if (int rc = set_smem(k_env_step_att<NK, MD>, smem)) return rc;                                           \
+        if (int rc = set_smem(k_env_step_att<NK, MD, TQ>, smem)) return rc;                                       \
         /* persistent grid: as many blocks as stay resident, each owning a contiguous range of envs */            \
         int dev = 0, sms = 0, bps = 0;                                                                            \
         CK(cudaGetDevice(&dev));                                                                                  \
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                    \
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD>, block, smem));             \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD, TQ>, block, smem));         \
         long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
         if (pgrid > (long long)grid) pgrid = grid;                                                                \
         const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
         pgrid = (B + per_block - 1) / per_block;                                                                  \
-        k_env_step_att<NK, MD><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
+        k_env_step_att<NK, MD, TQ><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
                                                          reward, terminated, truncated, inner_steps, B, env0, per_block, vx); \
     } else {                                                                                                      \
         if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                               \
         k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
                                                      reward, terminated, truncated, inner_steps, B, env0, vx);    \
     }
-    DISPATCH(nv.kind, dv.mode, 0, CALL);
+    DISPATCH(nv.kind, dv.mode, att ? nv.ts : 0, CALL);
 #undef CALL
     CK(cudaGetLastError());
     return PBN_OK;
