@@ -75,10 +75,15 @@ class PBNVectorEnv:
         self.ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self.final_obs = torch.zeros_like(self.sim.state)
         self._needs_reset = True
+        self._obs_bits = None
 
     # ---- observations -----------------------------------------------------------------------------------------
     def _obs(self, planes):
-        return planes if self.obs_mode == "packed" else self.sim.unpack(planes)
+        if self.obs_mode == "packed":
+            return planes
+        if self._obs_bits is None:  # owned by the env, overwritten by the next step (see the module docstring)
+            self._obs_bits = torch.empty((self.num_envs, self.n), dtype=torch.uint8, device=self.device)
+        return self.sim.unpack(planes, out=self._obs_bits)
 
     @property
     def state(self):
@@ -101,8 +106,7 @@ class PBNVectorEnv:
             raise RuntimeError("call reset() before step()")
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions))
-        actions = actions.to(self.device, dtype=torch.int32, non_blocking=True).reshape(self.num_envs, -1)
-        if actions.shape[1] != self.action_width:
+        if actions.numel() != self.num_envs * self.action_width:
             raise ValueError(f"actions must have shape [{self.num_envs}, {self.action_width}]")
         sim = self.sim
         # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)

@@ -203,3 +203,33 @@ def test_exhaustive_attractors_match_reference():
             want.append(states[pos:pos + sz])
             pos += sz
         assert got == want, k
+
+
+def test_logic_compiler_agrees_with_python_semantics():
+    """Random expressions over and/or/not/parentheses/True/False: the compiled closure tree == Python's own evaluation
+    (same precedence: not > and > or), for every assignment of the symbols."""
+    import itertools
+    import random as pyrandom
+
+    from gym_PBN.utils.logic.eval import LogicExpressionEvaluator, compile_expression
+
+    rnd = pyrandom.Random(7)
+    names = ["x1", "x2", "u", "geneA", "y10"]
+
+    def gen(depth):
+        if depth == 0 or rnd.random() < 0.25:
+            return rnd.choice(names + ["True", "False"])
+        kind = rnd.random()
+        if kind < 0.25:
+            return "not " + gen(depth - 1)
+        if kind < 0.45:
+            return "(" + gen(depth - 1) + ")"
+        return gen(depth - 1) + rnd.choice([" and ", " or "]) + gen(depth - 1)
+
+    for _ in range(300):
+        expr = gen(4)
+        fn = compile_expression(expr)
+        syms = sorted(set(LogicExpressionEvaluator.get_symbols(expr)))
+        for vals in itertools.product([False, True], repeat=len(syms)):
+            env = dict(zip(syms, vals))
+            assert bool(fn(env)) == bool(eval(expr, {"__builtins__": {}}, dict(env))), expr
