@@ -101,6 +101,18 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
                 rec[i * fmax + k] = make_uint2(packed, d->pr_lut[q]);
             }
         }
+        if (fmax <= 5) {  // mask table of the bit-sliced synchronous kernel
+            const int lrow = fmax * 16 + 4;  // +16 B per node: consecutive nodes (lanes) start in different bank groups
+            std::vector<u32> lm((size_t)n * lrow, 0u);
+            for (int i = 0; i < n; i++) {
+                const int q0 = d->pr_off[i], f = d->pr_off[i + 1] - q0;
+                for (int k = 0; k < fmax; k++) {
+                    const int q = q0 + (k < f ? k : f - 1);
+                    for (int b = 0; b < 16; b++) lm[(size_t)i * lrow + k * 16 + b] = ((d->pr_lut[q] >> b) & 1) ? 0xFFFFFFFFu : 0u;
+                }
+            }
+            rc |= upload(net->owned, lm.data(), lm.size(), &v.lutmask);
+        }
         const int np = d->pr_off[n];
         rc |= upload(net->owned, d->pr_off, (size_t)n + 1, &v.pr_off);
         rc |= upload(net->owned, d->pr_cum, (size_t)np, &v.pr_cum);
@@ -341,6 +353,115 @@ __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev,
 __device__ __forceinline__ void vec_flush_stats(const VecView &vx, unsigned long long *s_stats) {
     __syncthreads();
     if (vx.enabled && threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&vx.stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// ----------------------------------------------------------------------------------------------- K1 sync, bit-sliced
+// 32x32 bit-matrix transpose across a warp: afterwards lane i's bit j is what lane j's bit i was.
+__device__ __forceinline__ u32 warp_transpose32(u32 x, u32 lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const u32 m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const u32 y = __shfl_xor_sync(0xFFFFFFFFu, x, s);
+        x = (lane & s) ? (((y & ~m) >> s) | (x & ~m)) : ((x & m) | ((y & m) << s));
+    }
+    return x;
+}
+
+// Graph.synch_step (base.py:300-303) for 32 envs at a time: a WARP owns a group of 32 consecutive envs, the state is
+// held TRANSPOSED in shared memory (one 32-bit word per node, bit b = env b of the group), lane l computes the nodes
+// i = l, l+32, ...  The predictor choice of the 32 envs is one bit-serial comparison of 32 uniforms with the node's
+// thresholds (a fresh random word per bit level, levels stop when every env is decided: ~10 words instead of 32 draws),
+// every predictor is evaluated on all 32 envs with a 15-instruction mux tree over precomputed LUT masks.
+// Semantics restated in oracle/pbn_oracle.c: orc_rollout_sync_sliced.
+__global__ void __launch_bounds__(PBN_BLOCK) k_sync_sliced(NetView nv, DrawView dv, u32 *state, long long B, long long env0, int steps) {
+    const int n = nv.n, fmax = nv.fmax, w32 = nv.w32;
+    const int npad = w32 * 32;
+    unsigned char *blob = smem_raw;
+    u32 *lm = reinterpret_cast<u32 *>(smem_raw + nv.blob_bytes);
+    const int lrow = fmax * 16 + 4;
+    u32 *words = lm + (size_t)n * lrow;  // [8 warps][2][npad]
+    stage(blob, nv.blob, nv.blob_bytes);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(nv.lutmask);
+        uint4 *dst = reinterpret_cast<uint4 *>(lm);
+        for (int i = threadIdx.x; i < n * lrow / 4; i += PBN_BLOCK) dst[i] = src[i];
+    }
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const long long e0 = ((long long)blockIdx.x * (PBN_BLOCK / 32) + warp) * 32;  // first env of this warp's group
+    u32 *cur = words + warp * 2 * npad, *nxt = cur + npad;
+    const bool live = e0 < B;
+    if (live) {
+        const long long e = e0 + lane;
+        for (int w = 0; w < w32; w++) {
+            const u32 x = e < B ? state[(long long)w * B + e] : 0u;
+            cur[w * 32 + lane] = warp_transpose32(x, lane);
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    const u32 G = (u32)((unsigned long long)(env0 + e0) >> 5);
+    const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr);
+    const uint2 *rec = reinterpret_cast<const uint2 *>(blob + nv.off_rec);
+    for (int t = 0; t < steps; t++) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + (int)lane;
+            const bool valid = i < n;
+            const int ii = valid ? i : 0;
+            const uint4 T = thr[ii * nv.tsq_stride];
+            u32 T0 = T.x, T1 = T.y, T2 = T.z, T3 = T.w;
+            // a threshold of 2^31 (p = 1, and the padding of absent predictors) is "always below": decided at once
+            u32 lt0 = T0 >> 31 ? ~0u : 0u, lt1 = T1 >> 31 ? ~0u : 0u, lt2 = T2 >> 31 ? ~0u : 0u, lt3 = T3 >> 31 ? ~0u : 0u;
+            u32 u0 = ~lt0, u1 = ~lt1, u2 = ~lt2, u3 = ~lt3;
+            if (!valid) u0 = u1 = u2 = u3 = 0;
+            T0 <<= 1; T1 <<= 1; T2 <<= 1; T3 <<= 1;  // bit 30 -> sign position
+            u32 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+            for (int l = 0; l < 31; l++) {
+                if (!__any_sync(0xFFFFFFFFu, (u0 | u1 | u2 | u3) != 0u)) break;
+                if ((l & 3) == 0) philox4x32_10((u32)(l >> 2), dv.epoch, G, ((u32)t << 12) | (u32)ii, dv.seed_lo, dv.seed_hi, b0, b1, b2, b3);
+                const u32 R = b0;
+                b0 = b1; b1 = b2; b2 = b3;
+                const u32 s0 = (u32)((int)T0 >> 31), s1 = (u32)((int)T1 >> 31), s2 = (u32)((int)T2 >> 31), s3 = (u32)((int)T3 >> 31);
+                lt0 |= u0 & ~R & s0; u0 &= ~(R ^ s0);
+                lt1 |= u1 & ~R & s1; u1 &= ~(R ^ s1);
+                lt2 |= u2 & ~R & s2; u2 &= ~(R ^ s2);
+                lt3 |= u3 & ~R & s3; u3 &= ~(R ^ s3);
+                T0 <<= 1; T1 <<= 1; T2 <<= 1; T3 <<= 1;
+            }
+            if (valid) {
+                // predictor j is chosen where r >= T_{j-1} and r < T_j (absent thresholds are "always below")
+                const u32 c0 = lt0, c1 = lt1 & ~lt0, c2 = lt2 & ~lt1, c3 = lt3 & ~lt2, c4 = ~lt3;
+                u32 out = 0;
+                for (int j = 0; j < fmax; j++) {
+                    const u32 chosen = j == 0 ? c0 : j == 1 ? c1 : j == 2 ? c2 : j == 3 ? c3 : c4;
+                    const uint2 r = rec[i * fmax + j];
+                    const u32 x0 = cur[r.x & 0xFF], x1 = cur[(r.x >> 8) & 0xFF], x2 = cur[(r.x >> 16) & 0xFF], x3 = cur[r.x >> 24];
+                    const uint4 *M = reinterpret_cast<const uint4 *>(lm + (size_t)i * lrow + j * 16);
+                    const uint4 m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3];
+                    // 16 -> 8 on x3 (index bit 0), 8 -> 4 on x2, 4 -> 2 on x1, 2 -> 1 on x0
+                    const u32 a0 = (x3 & m0.y) | (~x3 & m0.x), a1 = (x3 & m0.w) | (~x3 & m0.z);
+                    const u32 a2 = (x3 & m1.y) | (~x3 & m1.x), a3 = (x3 & m1.w) | (~x3 & m1.z);
+                    const u32 a4 = (x3 & m2.y) | (~x3 & m2.x), a5 = (x3 & m2.w) | (~x3 & m2.z);
+                    const u32 a6 = (x3 & m3.y) | (~x3 & m3.x), a7 = (x3 & m3.w) | (~x3 & m3.z);
+                    const u32 d0 = (x2 & a1) | (~x2 & a0), d1 = (x2 & a3) | (~x2 & a2);
+                    const u32 d2 = (x2 & a5) | (~x2 & a4), d3 = (x2 & a7) | (~x2 & a6);
+                    const u32 g0 = (x1 & d1) | (~x1 & d0), g1 = (x1 & d3) | (~x1 & d2);
+                    out |= chosen & ((x0 & g1) | (~x0 & g0));
+                }
+                nxt[i] = out;
+            }
+        }
+        __syncwarp();
+        u32 *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    {
+        const long long e = e0 + lane;
+        for (int w = 0; w < w32; w++) {
+            u32 x = cur[w * 32 + lane];
+            if (w * 32 + (int)lane >= n) x = 0;
+            x = warp_transpose32(x, lane);
+            if (e < B) state[(long long)w * B + e] = x;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------- K2 env step
@@ -823,9 +944,24 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
     const NetView &nv = net->v;
     const DrawView dv = make_draws(draws);
     const int block = block_for(B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sync == 2) {  // bit-sliced synchronous mode
+        if (nv.kind != PBN_NET_PRED || !nv.lutmask || nv.ts != 4)
+            return fail(PBN_ERR_UNSUPPORTED, "bit-sliced synchronous mode needs a predictor network with at most 5 predictors per node");
+        if (dv.mode != PBN_DRAW_PHILOX) return fail(PBN_ERR_UNSUPPORTED, "bit-sliced synchronous mode has no replay source (use sync=1)");
+        if (env0 & 31) return fail(PBN_ERR_ARG, "env0 must be a multiple of 32: a group of 32 consecutive env ids shares the random words");
+        if (steps >= (1 << 20)) return fail(PBN_ERR_ARG, "at most 2^20 steps per launch");
+        const size_t sm = (size_t)nv.blob_bytes + (size_t)nv.n * (nv.fmax * 16 + 4) * 4 + (size_t)(PBN_BLOCK / 32) * 2 * nv.w32 * 32 * 4;
+        if (sm > 200 * 1024) return fail(PBN_ERR_UNSUPPORTED, "network too large for the bit-sliced tables");
+        if (int rc = set_smem(k_sync_sliced, sm)) return rc;
+        const long long groups = (B + 31) / 32;
+        const unsigned g2 = (unsigned)((groups + PBN_BLOCK / 32 - 1) / (PBN_BLOCK / 32));
+        k_sync_sliced<<<g2, PBN_BLOCK, sm, s>>>(nv, dv, state, B, env0, (int)steps);
+        CK(cudaGetLastError());
+        return PBN_OK;
+    }
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const size_t smem = (size_t)nv.blob_bytes + (size_t)2 * nv.w32 * block * 4;
-    cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                           \
     if (int rc = set_smem(k_rollout<NK, MD, TQ>, smem)) return rc;                 \
     k_rollout<NK, MD, TQ><<<grid, block, smem, s>>>(nv, dv, state, B, env0, steps, sync)

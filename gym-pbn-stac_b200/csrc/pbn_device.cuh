@@ -34,6 +34,8 @@ struct NetView {
     const int *pr_off;
     const double *pr_cum, *pr_codsum;
     const double *tt_prob;
+    // bit-sliced synchronous mode (predictor nets, fmax <= 5): u32 [N*fmax][16], entry k = all-ones iff LUT bit k is set
+    const u32 *lutmask;
 };
 
 // Packed env image: cubes as (care, value) word pairs.

@@ -171,9 +171,12 @@ class Simulator:
             self.launches += 1
 
     def rollout(self, steps, sync=False, replay=None):
+        """sync: False = asynchronous updates, True = Graph.synch_step per env, "sliced" = the same law computed for 32 envs
+        at a time on bit-sliced words (predictor networks with <= 5 predictors per node, Philox draws only)."""
         d = self._draws(replay)
+        mode = 2 if sync == "sliced" else int(bool(sync))
         with torch.cuda.device(self.device):
-            abi.check(abi.lib().pbn_rollout(self.net.handle, _ptr(self.state), self.B, self.env0, int(steps), int(bool(sync)),
+            abi.check(abi.lib().pbn_rollout(self.net.handle, _ptr(self.state), self.B, self.env0, int(steps), mode,
                                             C.byref(d), _stream()))
             self.launches += 1
 

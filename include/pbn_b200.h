@@ -108,7 +108,9 @@ typedef struct {
 } PbnDraws;
 
 /* K1 — `steps` updates of B envs in one launch, state resident on chip.
-   sync=0: PBN.step (common/pbn.py:88-92) / Graph.step (base.py:306-312); sync=1: Graph.synch_step (base.py:300-303). */
+   sync=0: PBN.step (common/pbn.py:88-92) / Graph.step (base.py:306-312); sync=1: Graph.synch_step (base.py:300-303);
+   sync=2: the same synchronous law, bit-sliced over groups of 32 consecutive env ids (predictor networks with at most
+   5 predictors per node, Philox draws, env0 % 32 == 0). */
 int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, int64_t steps, int32_t sync,
                 const PbnDraws *draws, void *stream);
 

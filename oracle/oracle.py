@@ -193,6 +193,15 @@ def rollout(net, state, steps, draws, sync=False, env0=0):
     return state
 
 
+def rollout_sync_sliced(net, state, steps, draws, env0=0):
+    state = np.ascontiguousarray(state, np.uint8)
+    rc = lib().orc_rollout_sync_sliced(C.byref(net.c), _p(state), C.c_int64(state.shape[0]), C.c_int64(env0), C.c_int64(steps),
+                                       C.byref(draws.c))
+    if rc:
+        raise ValueError(f"orc_rollout_sync_sliced: unsupported input (code {rc})")
+    return state
+
+
 def env_step(net, env, state, n_steps, target_att, actions, draws, env0=0):
     B = state.shape[0]
     actions = np.ascontiguousarray(actions, np.int32).reshape(B, -1)

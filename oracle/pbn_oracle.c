@@ -225,6 +225,73 @@ int orc_rollout(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, int6
     return 0;
 }
 
+/* K1, bit-sliced synchronous mode (PHILOX only, predictor graphs with at most 5 predictors per node).
+   Same law as Graph.synch_step (base.py:300-303): every node of every env is redrawn from the OLD state, predictor
+   chosen by cumulative COD weight.  Restated for groups of 32 consecutive global env ids handled as ONE 32-bit word
+   per node (bit b = env 32*G + b):
+     * the predictor choice of the 32 envs for node i at step t compares 32 independent 31-bit uniforms with the node's
+       thresholds bit-serially, most significant bit first: level l draws one word R (bit b = bit 30-l of env b's
+       uniform) from Philox4x32-10 with counter (l>>2, epoch, G, t<<12 | i), word l&3; for threshold T with bit 30-l set,
+       envs still undecided whose bit is 0 are decided "r < T", those with bit 1 stay undecided; with the bit clear,
+       undecided envs with bit 1 are decided "r >= T".  Levels stop as soon as no env is undecided for any threshold.
+     * predictor j is chosen where r >= T_{j-1} and r < T_j; the node's next word is OR_j (chosen_j & f_j(old words)). */
+int orc_rollout_sync_sliced(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, int64_t steps, const OrcDraws *dr) {
+    const int n = net->n;
+    if (net->kind != ORC_PRED || dr->mode != ORC_PHILOX || (env0 & 31)) return 1;
+    for (int i = 0; i < n; i++) if (net->pr_off[i + 1] - net->pr_off[i] > 5) return 2;
+    const int64_t groups = (B + 31) / 32;
+    const uint32_t key[2] = {(uint32_t)dr->seed, (uint32_t)(dr->seed >> 32)};
+#pragma omp parallel for schedule(static) if (B >= 256)
+    for (int64_t gi = 0; gi < groups; gi++) {
+        const int64_t gb = gi * 32;
+        const uint64_t G = (uint64_t)(env0 + gb) >> 5;
+        uint32_t *cur = (uint32_t *)calloc((size_t)n, 4), *nxt = (uint32_t *)calloc((size_t)n, 4);
+        for (int i = 0; i < n; i++)
+            for (int b = 0; b < 32 && gb + b < B; b++) cur[i] |= (uint32_t)state[(gb + b) * n + i] << b;
+        for (int64_t t = 0; t < steps; t++) {
+            for (int i = 0; i < n; i++) {
+                const int q0 = net->pr_off[i], f = net->pr_off[i + 1] - q0;
+                uint32_t lt[4] = {0, 0, 0, 0}, und[4] = {0, 0, 0, 0}, T[4] = {0, 0, 0, 0};
+                for (int k = 0; k < f - 1; k++) {
+                    T[k] = net->pr_thr[q0 + k];
+                    if (T[k] >= 0x80000000u) lt[k] = 0xFFFFFFFFu; else und[k] = 0xFFFFFFFFu;
+                }
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int l = 0; l < 31 && (und[0] | und[1] | und[2] | und[3]); l++) {
+                    if ((l & 3) == 0) {
+                        const uint32_t ctr[4] = {(uint32_t)(l >> 2), dr->epoch, (uint32_t)G, (uint32_t)((t << 12) | i)};
+                        orc_philox4x32_10(ctr, key, w);
+                    }
+                    const uint32_t R = w[l & 3];
+                    for (int k = 0; k < f - 1; k++) {
+                        if ((T[k] >> (30 - l)) & 1u) { lt[k] |= und[k] & ~R; und[k] &= R; }
+                        else und[k] &= ~R;
+                    }
+                }
+                uint32_t out = 0;
+                for (int j = 0; j < f; j++) {
+                    const uint32_t below = j < f - 1 ? lt[j] : 0xFFFFFFFFu;      /* r < T_j (the last predictor takes the rest) */
+                    const uint32_t not_prev = j > 0 ? ~lt[j - 1] : 0xFFFFFFFFu;  /* r >= T_{j-1} */
+                    const uint32_t chosen = below & not_prev;
+                    const int32_t *in = net->pr_in + 4 * (q0 + j);
+                    const uint32_t x0 = cur[in[0]], x1 = cur[in[1]], x2 = cur[in[2]], x3 = cur[in[3]];
+                    uint32_t fj = 0;
+                    for (int idx = 0; idx < 16; idx++)
+                        if ((net->pr_lut[q0 + j] >> idx) & 1)
+                            fj |= ((idx & 8) ? x0 : ~x0) & ((idx & 4) ? x1 : ~x1) & ((idx & 2) ? x2 : ~x2) & ((idx & 1) ? x3 : ~x3);
+                    out |= chosen & fj;
+                }
+                nxt[i] = out;
+            }
+            uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+        }
+        for (int i = 0; i < n; i++)
+            for (int b = 0; b < 32 && gb + b < B; b++) state[(gb + b) * n + i] = (uint8_t)((cur[i] >> b) & 1u);
+        free(cur); free(nxt);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ cube matching */
 static inline int cube_match(const int8_t *cube, const uint8_t *st, int n) {
     for (int i = 0; i < n; i++) if (cube[i] != 2 && cube[i] != (int8_t)st[i]) return 0;

@@ -551,3 +551,36 @@ def test_full_size_properties(eng):
     ohist = orc.ssd(onet, None, ost, iters, 0.01, tgt, orc.Draws(seed=42, epoch=1))
     assert np.array_equal(run(0, ob).astype(np.uint64), ohist)               # the first 2^14 chains, bit for bit
     assert _tv(full, ohist) < 0.06  # and the same law at 64x the width (noise floor of 2^14 short chains over 128 buckets ~0.04)
+
+
+@pytest.mark.parametrize("which,B", [("100_5_kmeans", 4096), ("200_5_kmeans", 1000), ("70_5_kmeans", 33), ("150_5_kmeans", 2049)])
+def test_sync_sliced_matches_oracle(eng, which, B):
+    """Bit-sliced synchronous kernel (32 envs per word, bit-serial threshold compare, mux-tree LUTs) == its restatement."""
+    net, onet = _nets(eng, which)
+    seed, env0 = 5, 96
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=env0)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0), env0=env0)
+    sim.rollout(9, sync="sliced")
+    orc.rollout_sync_sliced(onet, ost, 9, orc.Draws(seed=seed, epoch=1), env0=env0)
+    assert np.array_equal(_state_np(sim), ost)
+    sim.rollout(1, sync="sliced")
+    orc.rollout_sync_sliced(onet, ost, 1, orc.Draws(seed=seed, epoch=2), env0=env0)
+    assert np.array_equal(_state_np(sim), ost)
+
+
+def test_sync_sliced_split_invariance_and_errors(eng):
+    net, _ = _nets(eng, "100_5_kmeans")
+    full = eng.engine.Simulator(net, 640, seed=8, env0=0)
+    full.rand_state(); full.rollout(5, sync="sliced")
+    parts = []
+    for lo, hi in ((0, 320), (320, 640)):
+        s = eng.engine.Simulator(net, hi - lo, seed=8, env0=lo)
+        s.rand_state(); s.rollout(5, sync="sliced")
+        parts.append(_state_np(s))
+    assert np.array_equal(np.concatenate(parts), _state_np(full))
+    with pytest.raises(ValueError):
+        eng.engine.Simulator(net, 64, seed=8, env0=7).rollout(1, sync="sliced")
+    net28, _ = _nets(eng, "28_15_median")  # 15 predictors per node: not supported by the sliced kernel
+    with pytest.raises(eng.abi.PbnError):
+        eng.engine.Simulator(net28, 64, seed=8).rollout(1, sync="sliced")

@@ -108,3 +108,34 @@ def test_ssd_total_variation_vs_reference():
     print("TV floor (ref vs ref)", floor, "TV oracle vs ref", got)
     assert 0.002 < floor < 0.1
     assert got <= 3 * floor
+
+
+@pytest.mark.parametrize("sliced", [False, True])
+def test_sync_step_law(sliced):
+    """One synchronous step from a fixed state: P(node i becomes 1) = sum of the COD weights of the predictors that output 1
+    (bittner/base.py:89-119), for the per-env Philox path and for the bit-sliced restatement."""
+    sets, ids = orc.load_bittner("100_5_kmeans")
+    net = orc.net_from_predictor_sets(sets, ids)
+    n, B = net.n, 64000
+    rng = np.random.default_rng(1)
+    s0 = rng.integers(0, 2, n).astype(np.uint8)
+    st = np.tile(s0, (B, 1))
+    if sliced:
+        orc.rollout_sync_sliced(net, st, 1, orc.Draws(seed=9, epoch=0))
+    else:
+        orc.rollout(net, st, 1, orc.Draws(seed=9, epoch=0), sync=True)
+    a = net.a
+    worst = 0.0
+    for i in range(n):
+        q0, q1 = a["pr_off"][i], a["pr_off"][i + 1]
+        p1, prev = 0.0, 0.0
+        for q in range(q0, q1):
+            w = (a["pr_cum"][q] - prev) / a["pr_codsum"][i]
+            prev = a["pr_cum"][q]
+            ins = a["pr_in"][4 * q:4 * q + 4]
+            idx = (s0[ins[0]] << 3) | (s0[ins[1]] << 2) | (s0[ins[2]] << 1) | s0[ins[3]]
+            p1 += w * ((int(a["pr_lut"][q]) >> int(idx)) & 1)
+        got = st[:, i].mean()
+        sigma = np.sqrt(max(p1 * (1 - p1), 1e-9) / B)
+        worst = max(worst, abs(got - p1) / sigma if p1 not in (0.0, 1.0) else abs(got - p1) * 1e9)
+    assert worst < 5.0, worst
