@@ -420,3 +420,38 @@ def test_bittner28_default_attractors_are_exact():
     for a in (0, 5, 0, 17, 0):
         obs, r, term, trunc, info = env.step(a)
         assert core.is_attracting_state(obs) or info["inner_cap_hit"]
+
+
+def test_vector_env_multi_matches_oracle():
+    """PBNVectorEnv over PBNTargetMultiEnv (K = 3 action slots, tensor semantics = duplicates dropped), fused step + reset."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    z = load("b28_multi_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/BittnerMulti-28-v0", all_attractors=atts, max_inner_steps=48, horizon=9)
+    B, seed = 2048, 23
+    vec = PBNVectorEnv(env, B, seed=seed, action_slots=3, dedup=True)
+    obs, info = vec.reset()
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    oenv = orc.Env(orc.ENV_MULTI, 28, attractors=atts, horizon=9, max_inner=48, dedup=1)
+    ost = np.zeros((B, 28), np.uint8)
+    ons, ota = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    assert np.array_equal(obs.cpu().numpy(), ost) and np.array_equal(info["target_attractor"].cpu().numpy(), ota)
+    rng = np.random.default_rng(5)
+    for t in range(15):
+        act = rng.integers(0, 29, size=(B, 3)).astype(np.int32)
+        dup = rng.random(B) < 0.3
+        act[dup, 2] = act[dup, 0]
+        obs, rew, term, trunc, info = vec.step(torch.from_numpy(act))
+        oobs, orew, oterm, otrunc, oin = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + 2 * t))
+        assert np.array_equal(rew.cpu().numpy(), orew) and np.array_equal(term.cpu().numpy(), oterm.astype(bool))
+        assert np.array_equal(trunc.cpu().numpy(), otrunc.astype(bool)) and np.array_equal(info["inner_steps"].cpu().numpy(), oin)
+        assert np.array_equal(vec.sim.unpack(info["final_obs_packed"]).cpu().numpy(), oobs)
+        done = (oterm | otrunc).astype(np.uint8)
+        orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=2 + 2 * t), mask=done)
+        want = np.where(done[:, None].astype(bool), ost, oobs)  # reset envs observe their new state, the rest the step's obs
+        assert np.array_equal(obs.cpu().numpy(), want)
+    assert vec.stats.reduced()["env_steps"] == 15 * B
