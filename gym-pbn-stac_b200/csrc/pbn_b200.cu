@@ -25,6 +25,7 @@ static int fail(int code, const std::string &msg) {
             return fail(PBN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
     } while (0)
 
+int pbn_fail_(int code, const std::string &msg) { return fail(code, msg); }  // for the other translation units
 extern "C" const char *pbn_last_error(void) { return g_err.c_str(); }
 extern "C" const char *pbn_version(void) { return "pbn_b200 0.1 (sm_100a)"; }
 

@@ -36,6 +36,11 @@ class PbnDraws(C.Structure):
                 ("used", C.c_void_p)]
 
 
+class PbnFitDesc(C.Structure):
+    _fields_ = [("n_genes", C.c_int32), ("n_samples", C.c_int32), ("row_off", C.c_void_p), ("rows", C.c_void_p),
+                ("cod_rank", C.c_void_p)]
+
+
 class PbnVecState(C.Structure):
     _fields_ = [("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("stats", C.c_void_p), ("final_obs", C.c_void_p),
                 ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws)]
@@ -73,6 +78,10 @@ EXPORTS = {
     "pbn_fetch_host": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_fetch_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbn_fit_blocks": (C.c_int, [C.c_int32]),
+    "pbn_fit_scan_host": (C.c_int, [C.POINTER(PbnFitDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "pbn_fit_eval_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_issue_peak": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "pbn_last_error": (C.c_char_p, []),
     "pbn_version": (C.c_char_p, []),

@@ -213,9 +213,12 @@ class _BittnerTarget(PBNTargetEnv):
     _GOAL = None
 
     def _build(self, render_mode, render_no_cache, name, horizon, reward_config, end_episode_on_success, all_attractors,
-               max_inner_steps, device, seed):
+               max_inner_steps, device, seed, predictor_set=None):
+        # predictor_set: None = shipped set of this size if upstream ships one, else fit `{N}_3_median` on the GPU;
+        # "fit" = always the reference's route (bittner/utils.py:54-80); or the name of a shipped set
         graph = utils.spawn(file=self.genedata, total_genes=self.N, include_ids=self.includeIDs, bin_method="median",
-                            n_predictors=3, predictor_sets_path=self.predictor_sets_path, device=device, seed=seed)
+                            n_predictors=3, predictor_sets_path=self.predictor_sets_path, device=device, seed=seed,
+                            predictor_set=predictor_set)
         goal = dict(self._GOAL)
         goal["horizon"] = horizon
         PBNTargetEnv.__init__(self, graph, goal, render_mode, render_no_cache, name or self.NAME, reward_config,
@@ -234,9 +237,10 @@ class Bittner70(_BittnerTarget):
              "undesired_node_values": tuple()}
 
     def __init__(self, render_mode="human", render_no_cache=False, name=None, horizon=69, reward_config=None,
-                 end_episode_on_success=True, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None):
+                 end_episode_on_success=True, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None,
+                 predictor_set=None):
         self._build(render_mode, render_no_cache, name, horizon, reward_config, end_episode_on_success, all_attractors,
-                    max_inner_steps, device, seed)
+                    max_inner_steps, device, seed, predictor_set)
 
 
 class Bittner100(Bittner70):
@@ -257,9 +261,10 @@ class Bittner7(_BittnerTarget):
              "target_node_values": ((1, 1, 1, 1, 1, 1, 0),), "undesired_node_values": tuple()}
 
     def __init__(self, render_mode="human", render_no_cache=False, name=None, horizon=100, reward_config=None,
-                 end_episode_on_success=True, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None):
+                 end_episode_on_success=True, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None,
+                 predictor_set=None):
         self._build(render_mode, render_no_cache, name, horizon, reward_config, end_episode_on_success, all_attractors,
-                    max_inner_steps, device, seed)
+                    max_inner_steps, device, seed, predictor_set)
         self.target_nodes = sorted(_MELANOMA_7)  # pbn_target.py:534 (the seven melanoma genes, sorted)
         self.target_node_values = self.all_attractors[-1]
         self.target_attractor = len(self.all_attractors) - 1  # last one (pbn_target.py:534-536)
@@ -288,6 +293,7 @@ class Bittner28(Bittner7):
     NAME = "Bittner-28"
 
     def __init__(self, render_mode="human", render_no_cache=False, name="Bittner-28", horizon=100, reward_config=None,
-                 end_episode_on_success=False, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None):
+                 end_episode_on_success=False, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None, seed=None,
+                 predictor_set=None):
         super().__init__(render_mode, render_no_cache, name, horizon, reward_config, end_episode_on_success,
-                         all_attractors, max_inner_steps, device, seed)
+                         all_attractors, max_inner_steps, device, seed, predictor_set)

@@ -143,9 +143,10 @@ class _BittnerMulti(PBNTargetMultiEnv):
 
     def __init__(self, render_mode="human", render_no_cache=False, name=None, horizon=100, reward_config=None,
                  end_episode_on_success=True, all_attractors=None, max_inner_steps=DEFAULT_MAX_INNER, device=None,
-                 seed=None, sample_pair=False):
+                 seed=None, sample_pair=False, predictor_set=None):
         graph = utils.spawn(file=self.genedata, total_genes=self.N, include_ids=self.includeIDs, bin_method="median",
-                            n_predictors=3, predictor_sets_path=self.predictor_sets_path, device=device, seed=seed)
+                            n_predictors=3, predictor_sets_path=self.predictor_sets_path, device=device, seed=seed,
+                            predictor_set=predictor_set)
         goal = dict(self._GOAL)
         goal["horizon"] = horizon
         super().__init__(graph, goal, render_mode, render_no_cache, name or self.NAME, reward_config,

@@ -185,6 +185,37 @@ int pbn_stg_expand(const uint32_t *masks, int32_t n_nodes, const uint32_t *front
 int pbn_stg_walk(const uint32_t *masks, int32_t n_nodes, uint32_t start, int64_t steps, uint64_t seed, uint32_t *out,
                  void *stream);
 
+/* Network inference — the COD scan of the Bittner predictor-set fitter (gym_PBN/envs/bittner/gen/predictor_sets.py:
+   _gen_predictor_sets_gene :41-78, add_to_buff :80-102, gen_COD :105-124).  For every target gene the reference fits
+   every triple of other genes (every product of their duplicate rows, every target row) by least squares, rounds the
+   fitted values and keeps the n_predictors best coefficients of determination.  Rows are binary over <= 32 samples, so
+   a row is one 32-bit mask and the device solves each 4x4 fit in exact integer arithmetic (csrc/pbn_fit.cuh).
+     rows      [R] bit s = binarised expression of sample s; gene i owns rows row_off[i]..row_off[i+1]
+     cod_rank  [R][S+1] class of the COD a target row gets for k misclassified samples (0 = highest COD), tabulated on
+               the host with the reference's float expressions; classes are comparable across the rows of one gene
+   Keys (smaller = better): rank<<52 | a<<40 | b<<28 | c<<16 | y<<12 | sc with a<b<c indices into the gene list with
+   the target removed, y the target row, sc the index of the input-row product — the reference's visiting order, so ties
+   in COD resolve as its strict `<` does.  Per gene g only candidates with key > key_gt[g] and visiting order < arr_lt[g]
+   are considered (NULL = no filter).  top_keys receives [G][pbn_fit_blocks(G)][top_l] per-block winners (all-ones = empty).
+   Candidates whose rounded fit is decided by a fitted value of exactly one half (the reference's outcome then depends on
+   float noise) never enter top_keys; when tie_rank_le is given, those whose best case ranks <= tie_rank_le[g] are
+   written to tie_keys as (key with the best-case rank, gene) pairs, *n_ties = how many there were (may exceed tie_cap).
+   All pointers are HOST pointers; the call blocks.  kernel_ms (optional) = device time of the scan. */
+typedef struct {
+    int32_t n_genes;
+    int32_t n_samples;
+    const int32_t *row_off;   /* [G+1] */
+    const uint32_t *rows;     /* [R] */
+    const uint16_t *cod_rank; /* [R][S+1], values < 1024 */
+} PbnFitDesc;
+int pbn_fit_blocks(int32_t n_genes);
+int pbn_fit_scan_host(const PbnFitDesc *desc, int32_t top_l, const uint64_t *key_gt, const uint64_t *arr_lt,
+                      const uint16_t *tie_rank_le, uint64_t *top_keys, uint64_t *tie_keys, int64_t tie_cap,
+                      int64_t *n_ties, float *kernel_ms);
+/* The per-candidate solver run on the HOST for n candidates (masks4 = [n][4]: inputs a, b, c and the target row):
+   squared-error counts for both roundings.  A test hook for the exact arithmetic; the product never calls it. */
+int pbn_fit_eval_host(const uint32_t *masks4, int64_t n, int32_t n_samples, int32_t *k_lo, int32_t *k_hi);
+
 /* Small-transfer helpers for the single-env drop-in classes (one env.step = one launch + one read-back):
    pbn_upload enqueues a host->device copy on `stream`; pbn_fetch_host enqueues n device->host copies into one host
    buffer (concatenated in order) and waits for the stream — the reference hands back host values (NumPy arrays, ints,

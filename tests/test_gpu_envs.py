@@ -163,8 +163,9 @@ def test_make_bittner_100_and_200_default_attractors():
     assert env.unwrapped.graph.N == 199
     env.reset(seed=2)
     env.step(0)
+    # sizes upstream ships no set for are fitted on the GPU (tests/test_gpu_fit.py); naming a set that does not exist raises
     with pytest.raises(FileNotFoundError):
-        gym_PBN.make("gym-PBN/Bittner-7-v0")
+        gym_PBN.make("gym-PBN/Bittner-100-v0", predictor_set="100_9_median")
 
 
 def test_multi_env_list_and_tensor_actions():
