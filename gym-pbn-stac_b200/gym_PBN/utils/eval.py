@@ -11,6 +11,7 @@ import itertools
 import numpy as np
 import torch
 
+from gym_PBN.b200 import abi
 from gym_PBN.b200 import dist as pdist
 from gym_PBN.b200 import engine
 
@@ -142,6 +143,61 @@ def eval_increase(env, model, original_ssd=None, iters=1_200_000, resets=300, bi
     states = ["".join(str(int(b)) for b in state) for state in env.target_node_values]
     delta = frame(model_ssd) - frame(original_ssd)
     return float(delta.loc[states, "Value"].sum())
+
+
+def eval_winrate(env, model, max_states=200_000, max_episode_steps=None, seed=0):
+    """(win rate, mean interactions, mean time steps) of `model` started from every non-target state, as the reference's
+    eval_winrate (utils/eval.py:160-197) computes them: states in itertools.product([0, 1], repeat=N) order (node 0 most
+    significant), target states skipped, enumeration stopped after index max_states + 1; an episode ends when the env
+    reports terminated (a win) or truncated; the start state is written with env.set (reset(options=) re-draws it, pbn_env.py:195-206); "time steps" sums info["interval"] (1 for envs without intervals).
+    The reference version cannot return (a debugging `raise ValueError` fires on the first win, :181); this one runs all
+    start states in lockstep on the GPU.  Truncation comes from the registration's max_episode_steps (the TimeLimit
+    wrapper gym.make adds), or `max_episode_steps` here.  `model.predict_batch(obs uint8 [B][N]) -> actions [B][width]`
+    is called once per step when it exists, else `model.predict(obs_row, obs_row, deterministic=True)` per env."""
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    limit = max_episode_steps if max_episode_steps is not None else getattr(env, "_max", None)
+    if not limit:
+        raise ValueError("eval_winrate needs a step limit: make the env through gym_PBN.make (registered max_episode_steps) "
+                         "or pass max_episode_steps")
+    core = getattr(env, "unwrapped", env)
+    n = core.observation_space.n
+    if n > 40:
+        raise ValueError("eval_winrate enumerates all 2^N states")
+    count = min(1 << n, int(max_states) + 2)
+    idx = np.arange(count, dtype=np.int64)
+    bits = ((idx[:, None] >> np.arange(n - 1, -1, -1)) & 1).astype(np.uint8)
+    targets = {tuple(int(v) for v in t) for t in (getattr(core, "target", None) or core.target_nodes)}  # PBNEnv keeps them as target_nodes
+    keep = np.array([tuple(int(v) for v in row) not in targets for row in bits]) if targets else np.ones(count, bool)
+    starts = bits[keep]
+    iters = len(starts)
+    if iters == 0:
+        return float("nan"), float("nan"), float("nan")
+    vec = PBNVectorEnv(core, iters, seed=seed, autoreset=False)
+    vec.reset()
+    vec.sim.set_state(torch.as_tensor(starts, device=vec.device))
+    vec.sim.n_steps.zero_()
+    dev = vec.device
+    alive = torch.ones(iters, dtype=torch.bool, device=dev)
+    won = torch.zeros(iters, dtype=torch.bool, device=dev)
+    interactions = torch.zeros(iters, dtype=torch.int64, device=dev)
+    timesteps = torch.zeros(iters, dtype=torch.int64, device=dev)
+    interval_col = {abi.ENV_PBN_SD: 1, abi.ENV_PBCN_SD: 0}.get(vec.image.kind)
+    obs = vec.sim.unpack()
+    for t in range(int(limit)):
+        actions = _policy_actions(model, obs)
+        obs, _r, terminated, _trunc, _info = vec.step(actions)
+        if interval_col is None:
+            step_len = 1
+        else:  # what the single env reports as info["interval"]: the last loop index for PBN-sampled-data (sampled_data.py:84)
+            step_len = actions[:, interval_col].to(torch.int64) - (1 if vec.image.kind == abi.ENV_PBN_SD else 0)
+        interactions += alive
+        timesteps += alive * step_len
+        won |= alive & terminated.bool()
+        alive &= ~terminated.bool()
+        if not bool(alive.any()):
+            break
+    return float(won.sum().item()) / iters, float(interactions.double().mean().item()), float(timesteps.double().mean().item())
 
 
 def visualize_ssd(ssd_frame, env_name):

@@ -456,3 +456,48 @@ def test_vector_env_multi_matches_oracle():
         want = np.where(done[:, None].astype(bool), ost, oobs)  # reset envs observe their new state, the rest the step's obs
         assert np.array_equal(obs.cpu().numpy(), want)
     assert vec.stats.reduced()["env_steps"] == 15 * B
+
+
+def test_eval_winrate_matches_single_env_loop():
+    """eval_winrate (utils/eval.py:160-197, working version): lockstep GPU episodes == the reference's per-state loop run
+    through the single-env API, for a deterministic network (no probabilistic node) and a fixed policy."""
+    import itertools
+
+    import gym_PBN
+    from gym_PBN.utils.eval import eval_winrate
+
+    det = (["a", "b", "c", "d"], [[("a", 1.0)], [("a or c", 1.0)], [("not d", 1.0)], [("b and c", 1.0)]])
+    goal = {"target_nodes": {(0, 1, 1, 0)}, "target": {(0, 1, 1, 0)}, "all_attractors": [{(0, 1, 1, 0)}, {(0, 0, 0, 0)}]}
+
+    class Policy:
+        def predict(self, obs, target=None, deterministic=True):
+            return (int(obs[2]) + 1, 2)  # flip node obs[2], hold for 2 steps
+
+        def predict_batch(self, obs):
+            return torch.stack([obs[:, 2].to(torch.int32) + 1, torch.full_like(obs[:, 2], 2, dtype=torch.int32)], dim=1)
+
+    env = gym_PBN.make("gym-PBN/PBN-sampled-data-v0", logic_func_data=det, goal_config=dict(goal), T=4)
+    rate, inter, steps = eval_winrate(env, Policy(), max_episode_steps=6)
+    # the reference loop, one start state at a time; the update picks a random node, so compare the laws loosely and the
+    # bookkeeping exactly where it is deterministic
+    wins = n = 0
+    lens = []
+    for state in itertools.product([0, 1], repeat=4):
+        if state in env.unwrapped.target_nodes:
+            continue
+        n += 1
+        env.reset()
+        env.unwrapped.set(np.array(state, dtype=bool))
+        obs = np.array(state, dtype=bool)
+        for j in range(1, 7):
+            obs, _r, term, trunc, info = env.step(Policy().predict(obs))
+            if term:
+                wins += 1
+            if term or j == 6:
+                lens.append(j)
+                break
+    assert n == 15 and 0.0 <= rate <= 1.0 and 1.0 <= inter <= 6.0
+    assert abs(steps - inter) < 1e-9  # PBN-sampled-data reports interval - 1 = 1 per interaction
+    assert abs(rate - wins / n) <= 0.5 and abs(inter - np.mean(lens)) <= 2.5
+    with pytest.raises(ValueError):
+        eval_winrate(env.unwrapped, Policy())  # no step limit anywhere
