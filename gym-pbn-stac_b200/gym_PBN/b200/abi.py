@@ -78,7 +78,6 @@ EXPORTS = {
     "pbn_fetch_host": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_fetch_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pbn_fit_blocks": (C.c_int, [C.c_int32]),
     "pbn_fit_scan_host": (C.c_int, [C.POINTER(PbnFitDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "pbn_fit_eval_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -23,6 +23,8 @@ def _family(env):
     from gym_PBN.envs.pbn_target import PBNTargetEnv
     from gym_PBN.envs.pbn_target_multi import PBNTargetMultiEnv
 
+    if "SelfTriggering" in type(env).__name__:
+        raise TypeError("self-triggering envs draw their interval per step on the host (self_triggering.py:79,181) and are not vectorised")
     if isinstance(env, PBNTargetMultiEnv):
         return "multi"
     if isinstance(env, PBNTargetEnv):
@@ -56,7 +58,7 @@ class PBNVectorEnv:
         self.max_inner_steps = int(max_inner_steps if max_inner_steps is not None else getattr(env, "max_inner_steps", 1))
         self.action_slots = action_slots
         if self.family == "pbn":
-            kind = next(v for k, v in _KIND_OF.items() if k in [c.__name__ for c in type(env).__mro__])
+            kind = next(_KIND_OF[c.__name__] for c in type(env).__mro__ if c.__name__ in _KIND_OF)  # most derived class first
             self.image = engine.EnvImage(
                 self.network, kind, attractors=[sorted(a) for a in env.all_attractors], targets=sorted(env.target_nodes),
                 n_control=getattr(env.PBN, "M", 0), control_write=getattr(env.PBN, "control_mode", "stac") == "write",

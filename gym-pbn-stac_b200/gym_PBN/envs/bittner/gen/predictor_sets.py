@@ -3,7 +3,7 @@
 For every gene the reference scores every triple of other genes by the coefficient of determination of a rounded
 least-squares fit (gen_COD, :105-124) and keeps the best `n_predictors` in a small buffer (add_to_buff, :80-102).
 Here the scan over all candidates runs on the GPU (`pbn_fit_scan_host`, csrc/pbn_fit.cu: one 32-bit mask per gene row,
-exact integer least squares, per-thread top lists merged per block); the host only
+exact integer least squares, per-thread top lists merged per block and per gene); the host only
   * tabulates, per target row, the COD of "k misclassified samples" with the reference's own float expressions,
   * settles the few candidates whose rounding the reference leaves to float noise (a fitted value of exactly 1/2),
   * recomputes (COD, A) of the winners with the reference's float expressions (pinv), because A is stored in the
@@ -145,8 +145,7 @@ def _scan(table, rank, top_l, key_gt=None, arr_lt=None, tie_le=None, tie_cap=1 <
     G = len(table.genes)
     lib = abi.lib()
     desc = abi.PbnFitDesc(G, table.n_samples, table.row_off.ctypes.data, table.masks.ctypes.data, rank.ctypes.data)
-    n_blk = lib.pbn_fit_blocks(G)
-    top = np.empty((G, n_blk, top_l), np.uint64)
+    top = np.empty((G, top_l), np.uint64)
     ms = C.c_float(0)
     as_ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
     while True:
@@ -159,8 +158,7 @@ def _scan(table, rank, top_l, key_gt=None, arr_lt=None, tie_le=None, tie_cap=1 <
         tie_cap = int(n_ties.value) + 1024  # rare: rerun with room for every reported candidate
     keys = []
     for g in range(G):
-        k = np.sort(top[g].reshape(-1))
-        keys.append([int(v) for v in k[:top_l] if v != KEY_NONE])
+        keys.append([int(v) for v in top[g] if v != KEY_NONE])
     tie_list = [] if ties is None else [(int(k), int(g)) for k, g in ties[: n_ties.value]]
     return keys, tie_list, ms.value
 

@@ -196,7 +196,7 @@ int pbn_stg_walk(const uint32_t *masks, int32_t n_nodes, uint32_t start, int64_t
    Keys (smaller = better): rank<<52 | a<<40 | b<<28 | c<<16 | y<<12 | sc with a<b<c indices into the gene list with
    the target removed, y the target row, sc the index of the input-row product — the reference's visiting order, so ties
    in COD resolve as its strict `<` does.  Per gene g only candidates with key > key_gt[g] and visiting order < arr_lt[g]
-   are considered (NULL = no filter).  top_keys receives [G][pbn_fit_blocks(G)][top_l] per-block winners (all-ones = empty).
+   are considered (NULL = no filter).  top_keys receives the [G][top_l] winners in ascending key order (all-ones = empty).
    Candidates whose rounded fit is decided by a fitted value of exactly one half (the reference's outcome then depends on
    float noise) never enter top_keys; when tie_rank_le is given, those whose best case ranks <= tie_rank_le[g] are
    written to tie_keys as (key with the best-case rank, gene) pairs, *n_ties = how many there were (may exceed tie_cap).
@@ -208,7 +208,6 @@ typedef struct {
     const uint32_t *rows;     /* [R] */
     const uint16_t *cod_rank; /* [R][S+1], values < 1024 */
 } PbnFitDesc;
-int pbn_fit_blocks(int32_t n_genes);
 int pbn_fit_scan_host(const PbnFitDesc *desc, int32_t top_l, const uint64_t *key_gt, const uint64_t *arr_lt,
                       const uint16_t *tie_rank_le, uint64_t *top_keys, uint64_t *tie_keys, int64_t tie_cap,
                       int64_t *n_ties, float *kernel_ms);

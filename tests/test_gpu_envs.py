@@ -496,7 +496,7 @@ def test_eval_winrate_matches_single_env_loop():
             if term or j == 6:
                 lens.append(j)
                 break
-    assert n == 15 and 0.0 <= rate <= 1.0 and 1.0 <= inter <= 6.0
+    assert n == 16 - len(env.unwrapped.target_nodes) and 0.0 <= rate <= 1.0 and 1.0 <= inter <= 6.0
     assert abs(steps - inter) < 1e-9  # PBN-sampled-data reports interval - 1 = 1 per interaction
     assert abs(rate - wins / n) <= 0.5 and abs(inter - np.mean(lens)) <= 2.5
     with pytest.raises(ValueError):

@@ -65,6 +65,7 @@ def compare(sets, ref, table):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--oracle-genes", type=int, default=4)
+    ap.add_argument("--only", type=int, default=0, help="fit just the {N}_3_median configuration (profiling)")
     args = ap.parse_args()
     out = {}
     meta = json.load(open(utils.DATA / "node_ids.json"))
@@ -93,28 +94,15 @@ def main():
         print(name, json.dumps(rec), file=sys.stderr, flush=True)
         return sets
 
+    if args.only:
+        _i, ids, _n, values = utils.prepare_gene_table(utils.DATA / "genedata.xls", args.only, M7, "median")
+        run(f"b{args.only}_3_median", ps.GeneTable(ids, values), 3)
+        print(json.dumps(out))
+        return
     _i, ids, _n, values = utils.prepare_gene_table(utils.DATA / "genedata.xls", 28, B28, "median")
     table = ps.GeneTable(ids, values)
     ref = pickle.load(open(utils.DATA / "predictor_sets_28_15_median.pkl", "rb"))
     run("b28_15_median", table, 15, ref, args.oracle_genes, ids, values)
-
-    z = np.load(ROOT / "tests" / "golden" / "fit_binned_70_csv.npz")
-    # the csv was written BEFORE drop_duplicates (tests/test_bittner.py:70); redo that step with the clone names
-    from gym_PBN.envs.bittner.gen import xls
-    all_ids, all_names, _r, _w = xls.read_gene_data(utils.DATA / "genedata.xls")
-    sel = np.concatenate([np.nonzero(all_ids == g)[0] for g in dict.fromkeys(z["ids"].tolist())])
-    assert (all_ids[sel] == z["ids"]).all()
-    seen, keep = set(), []
-    for j, r in enumerate(sel):
-        sig = (all_names[r],) + tuple(z["values"][j].tolist())
-        if sig not in seen:
-            seen.add(sig)
-            keep.append(j)
-    z = dict(ids=z["ids"][keep], values=z["values"][keep])
-    table = ps.GeneTable(z["ids"], z["values"].astype(np.int64))
-    print("csv genes == shipped 70 order:", table.genes == meta["70_5_kmeans"]["node_ids"], file=sys.stderr)
-    ref = pickle.load(open(utils.DATA / "predictor_sets_70_5_kmeans.pkl", "rb"))
-    run("b70_5_csv", table, 5, ref if len(ref) == len(table.genes) else None, 2, z["ids"], z["values"].astype(np.int64))
 
     for n in (7, 10, 30, 50, 70, 100, 200):
         inc = sorted(M7) if n == 7 else M7
