@@ -719,11 +719,52 @@ __device__ __forceinline__ u32 warp_scan_add(u32 v) {
 // The SSD iteration loop of one warp.  FULL = every lane owns a chain (all warps but possibly the last of the job).
 // PHILOX perturbation: ONE Bernoulli(p) renewal process per group of 32 consecutive chains over the interleaved index
 // c = node*32 + lane (window = 32*n positions per iteration).  Each round every lane draws one geometric gap from its
-// own stream, a warp prefix sum turns the 32 gaps into 32 event positions, and an event inside the current window flips
-// bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n independent Bernoulli(p) per chain per
-// iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
+// own PERTURBATION stream (block indices from 2^31 on), a warp prefix sum turns the 32 gaps into 32 event positions, and
+// an event inside the current window flips bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n
+// independent Bernoulli(p) per chain per iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
+// The UPDATE stream is then consumed at exactly two words per update, so when every iteration is one update (no
+// attractor loop) a Philox block serves two iterations with no buffer bookkeeping (STATIC path below).
+struct SsdPerturb {
+    u32 evp;      // this lane's pending event, relative to the window start (0xFFFFFFFF = none)
+    u32 last_p1;  // (position of the last generated event) + 1, relative to the window start
+};
+
+template <bool FULL>
+__device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, char *warp_cols, u32 W, float inv, u32 nvalid) {
+    for (;;) {
+        if (ps.evp < W) {
+            const u32 tl = ps.evp & 31u;
+            // word (node>>5) of column tl: byte offset = tl*4 + (node>>5)*1024, node = evp>>5
+            if (FULL || tl < nvalid)
+                atomicXor(reinterpret_cast<u32 *>(warp_cols + tl * 4u + ((ps.evp >> 10) << 10)), 1u << ((ps.evp >> 5) & 31u));
+            ps.evp = 0xFFFFFFFFu;
+        }
+        if (ps.last_p1 > W) break;  // the last generated event lies beyond this window
+        const u32 pre = warp_scan_add(1u + geom_gap(dp.next(), inv));
+        ps.evp = ps.last_p1 - 1u + pre;
+        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+    }
+    if (ps.evp != 0xFFFFFFFFu) ps.evp -= W;
+    ps.last_p1 -= W;
+    __syncwarp();
+}
+
+struct SsdCount {
+    int cur;
+    u32 run;
+};
+__device__ __forceinline__ void ssd_count(SsdCount &c, const SsdLoopArgs &a, const Col &st) {
+    const int b = ssd_bucket(a.sp, a.s_tgt, st);
+    if (b != c.cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
+        if (a.sp.smem_hist) atomicAdd(&a.shist[c.cur], c.run);
+        else atomicAdd(&a.hist[c.cur], (unsigned long long)c.run);
+        c.cur = b; c.run = 0;
+    }
+    c.run++;
+}
+
 template <int NET, int MODE, int TQ, bool HAS_ENV, bool FULL>
-__device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Draw<MODE> &d) {
+__device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Draw<MODE> &d, Draw<MODE> &dp) {
     const NetView &nv = a.nv;
     const SsdParams &sp = a.sp;
     const u32 lane = threadIdx.x & 31u;
@@ -731,44 +772,37 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
     const u32 n = (u32)nv.n, W = n * 32u;
     const float inv = sp.inv;
     const bool flips = inv <= 0.f;
-    u32 evp = 0xFFFFFFFFu;  // this lane's pending event, relative to the window start (none)
-    u32 last_p1 = 0;        // (position of the last generated event) + 1, relative to the window start
+    SsdPerturb ps{0xFFFFFFFFu, 0u};
     char *warp_cols = reinterpret_cast<char *>(a.sst + (threadIdx.x & ~31u));
-    int cur = active ? ssd_bucket(sp, a.s_tgt, st) : 0;
-    u32 run = 0;
-    for (int t = 0; t < a.iters; t++) {
-        if (active) {
-            const int b = ssd_bucket(sp, a.s_tgt, st);
-            if (b != cur) {  // run-length aggregated histogram update (a chain rarely changes bucket)
-                if (sp.smem_hist) atomicAdd(&a.shist[cur], run);
-                else atomicAdd(&a.hist[cur], (unsigned long long)run);
-                cur = b; run = 0;
-            }
-            run++;
+    SsdCount cnt{active ? ssd_bucket(sp, a.s_tgt, st) : 0, 0u};
+    int t = 0;
+    if constexpr (MODE == PBN_DRAW_PHILOX && !HAS_ENV && FULL) {
+        // STATIC path: one Philox block of the update stream per two iterations, words used in stream order
+        u32 ublk = 0;
+        for (; t + 1 < a.iters; t += 2) {
+            u32 x0, x1, x2, x3;
+            philox4x32_10(ublk, d.c1, d.c2, d.c3, d.k0, d.k1, x0, x1, x2, x3);
+            ublk++;
+            ssd_count(cnt, a, st);
+            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, 32u);
+            micro_step_words<NET, TQ>(nv, a.blob, st, x0, x1, d);
+            __syncwarp();  // updates land before the next iteration's cross-lane flips
+            ssd_count(cnt, a, st);
+            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, 32u);
+            micro_step_words<NET, TQ>(nv, a.blob, st, x2, x3, d);
+            __syncwarp();
         }
+        d.blk = ublk;  // the stream object takes over where the static part stopped (block boundary)
+        d.have = 0;
+    }
+    for (; t < a.iters; t++) {
+        if (active) ssd_count(cnt, a, st);
         if constexpr (MODE == PBN_DRAW_REPLAY) {
             if (active)
                 for (u32 j = 0; j < n; j++)
                     if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
         } else {
-            if (flips) {
-                for (;;) {
-                    if (evp < W) {
-                        const u32 tl = evp & 31u;
-                        // word (node>>5) of column tl: byte offset = tl*4 + (node>>5)*1024, node = evp>>5
-                        if (FULL || tl < a.nvalid)
-                            atomicXor(reinterpret_cast<u32 *>(warp_cols + tl * 4u + ((evp >> 10) << 10)), 1u << ((evp >> 5) & 31u));
-                        evp = 0xFFFFFFFFu;
-                    }
-                    if (last_p1 > W) break;  // the last generated event lies beyond this window
-                    const u32 pre = warp_scan_add(1u + geom_gap(d.next(), inv));
-                    evp = last_p1 - 1u + pre;
-                    last_p1 = __shfl_sync(0xFFFFFFFFu, evp, 31) + 1u;
-                }
-                if (evp != 0xFFFFFFFFu) evp -= W;
-                last_p1 -= W;
-                __syncwarp();
-            }
+            if (flips) ssd_perturb<FULL>(ps, dp, warp_cols, W, inv, a.nvalid);
         }
         if (active) {
             micro_step<NET, MODE, TQ>(nv, a.blob, st, d);  // env.step(0): pbn_target.py:269-271
@@ -784,9 +818,9 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
         }
         if constexpr (MODE == PBN_DRAW_PHILOX) __syncwarp();  // updates land before the next iteration's cross-lane flips
     }
-    if (active && run) {
-        if (sp.smem_hist) atomicAdd(&a.shist[cur], run);
-        else atomicAdd(&a.hist[cur], (unsigned long long)run);
+    if (active && cnt.run) {
+        if (sp.smem_hist) atomicAdd(&a.shist[cnt.cur], cnt.run);
+        else atomicAdd(&a.hist[cnt.cur], (unsigned long long)cnt.run);
     }
 }
 
@@ -825,12 +859,13 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
     // warp-cooperative perturbation stream but own no state
     const long long warp_left = chains - (e - (threadIdx.x & 31));
     if (warp_left > 0) {
-        Draw<MODE> d;
+        Draw<MODE> d, dp;
         d.init(dv, e, env0 + e);
+        dp.init_perturb(dv, e, env0 + e);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
         SsdLoopArgs a{nv, ev, sp, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid};
-        if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d);   // every lane owns a chain: no predication
-        else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d);
+        if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d, dp);   // every lane owns a chain: no predication
+        else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d, dp);
         if (active) {
             store_state(st, state, chains, e, w32);
             d.done(dv, e);

@@ -77,6 +77,8 @@ __device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u3
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
+#define PBN_PERTURB_BLOCK0 0x80000000u
+
 template <int MODE>
 struct Draw;
 
@@ -85,11 +87,18 @@ struct Draw<PBN_DRAW_PHILOX> {
     u32 k0, k1, blk, c1, c2, c3;
     u32 b0, b1, b2, b3;
     int have;
+    u32 base;  // first block index of this stream: 0 = the env's update stream, PBN_PERTURB_BLOCK0 = its perturbation stream
     __device__ __forceinline__ void init(const DrawView &dv, long long /*local*/, long long env_id) {
         k0 = dv.seed_lo; k1 = dv.seed_hi;
-        blk = 0; c1 = dv.epoch; c2 = (u32)env_id; c3 = (u32)((u64)env_id >> 32);
+        blk = base = 0; c1 = dv.epoch; c2 = (u32)env_id; c3 = (u32)((u64)env_id >> 32);
         have = 0;
         b0 = b1 = b2 = b3 = 0;
+    }
+    // second stream of the same env (SSD perturbation gaps): same key and counter words, block indices from 2^31 on, so
+    // the update stream is consumed at a fixed rate (two draws per update) whatever the perturbations need
+    __device__ __forceinline__ void init_perturb(const DrawView &dv, long long local, long long env_id) {
+        init(dv, local, env_id);
+        blk = base = PBN_PERTURB_BLOCK0;
     }
     __device__ __forceinline__ u32 next() {
         if (have == 0) {
@@ -102,7 +111,7 @@ struct Draw<PBN_DRAW_PHILOX> {
         have--;
         return r;
     }
-    __device__ __forceinline__ u32 consumed() const { return blk * 4u - (u32)have; }  // draws taken so far
+    __device__ __forceinline__ u32 consumed() const { return (blk - base) * 4u - (u32)have; }  // draws taken so far
     // uniform integer in [lo, lo+n): random.randint(lo, lo+n-1)
     __device__ __forceinline__ int randint(int lo, int n) { return lo + (int)__umulhi(next(), (u32)n); }
     __device__ __forceinline__ void done(const DrawView &dv, long long local) {
@@ -137,6 +146,8 @@ struct Draw<PBN_DRAW_REPLAY> {
         dp = dv.dbls + local * dv.dbl_stride;
         ni = nd = 0;
     }
+    __device__ __forceinline__ void init_perturb(const DrawView &dv, long long local, long long env_id) { init(dv, local, env_id); }
+    __device__ __forceinline__ u32 next() { return 0u; }  // never drawn from in replay mode (flips replay float64 draws)
     __device__ __forceinline__ int randint(int /*lo*/, int /*n*/) { ni++; return *ip++; }  // recorded result
     __device__ __forceinline__ double dbl() { nd++; return *dp++; }
     __device__ __forceinline__ void done(const DrawView &dv, long long local) {
@@ -200,10 +211,11 @@ struct Col {
 // bittner/base.py:89-119 Node.Predstep.  `blob` is the shared-memory copy of the network image.
 // TQ = number of threshold quads per node known at compile time (1: up to 5 predictors), 0 = read nv.ts at run time
 template <int MODE, int TQ>
-__device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
+__device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d,
+                                         u32 word = 0, bool have_word = false) {
     int j;
     if constexpr (MODE == PBN_DRAW_PHILOX) {
-        u32 r = d.next() >> 1;
+        u32 r = (have_word ? word : d.next()) >> 1;
         const int nq = TQ > 0 ? TQ : (nv.ts >> 2);
         const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * nv.tsq_stride;
         j = 0;
@@ -237,7 +249,8 @@ __device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char 
 
 // common/node.py:31-38 Node.compute_next_value
 template <int MODE>
-__device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
+__device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d,
+                                       u32 word = 0, bool have_word = false) {
     uint2 nr = reinterpret_cast<const uint2 *>(blob + nv.off_node)[i];
     const unsigned short *in = reinterpret_cast<const unsigned short *>(blob + nv.off_in) + (nr.y & 0xFFFF);
     int k = (int)(nr.y >> 16);
@@ -245,16 +258,26 @@ __device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *b
     for (int q = 0; q < k; q++) idx = (idx << 1) | st.bit(in[q]);
     if constexpr (MODE == PBN_DRAW_PHILOX) {
         u32 thr = reinterpret_cast<const u32 *>(blob + nv.off_thr)[nr.x + idx];
-        return ((d.next() >> 1) < thr) ? 1u : 0u;
+        return (((have_word ? word : d.next()) >> 1) < thr) ? 1u : 0u;
     } else {
         return (d.dbl() < nv.tt_prob[nr.x + idx]) ? 1u : 0u;  // u < p, node.py:37-38
     }
 }
 
 template <int NET, int MODE, int TQ>
-__device__ __forceinline__ u32 node_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d) {
-    if constexpr (NET == PBN_NET_PRED) return pred_next<MODE, TQ>(nv, blob, st, i, d);
-    else return tt_next<MODE>(nv, blob, st, i, d);
+__device__ __forceinline__ u32 node_next(const NetView &nv, const unsigned char *blob, const Col &st, int i, Draw<MODE> &d,
+                                         u32 word = 0, bool have_word = false) {
+    if constexpr (NET == PBN_NET_PRED) return pred_next<MODE, TQ>(nv, blob, st, i, d, word, have_word);
+    else return tt_next<MODE>(nv, blob, st, i, d, word, have_word);
+}
+
+// the same update from two given 32-bit words of the env's update stream (Philox mode): wa picks the node, wb decides
+template <int NET, int TQ = 0>
+__device__ __forceinline__ void micro_step_words(const NetView &nv, const unsigned char *blob, const Col &st, u32 wa, u32 wb,
+                                                 Draw<PBN_DRAW_PHILOX> &d) {
+    const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
+    const u32 v = node_next<NET, PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, d, wb, true);
+    st.put(i, v);
 }
 
 // one asynchronous update: PBN.step common/pbn.py:88-92 / PBCN.step common/pbcn.py:59-61 / Graph.step base.py:306-312

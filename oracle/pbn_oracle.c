@@ -472,7 +472,8 @@ int orc_rand_state(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, c
    REPLAY: n doubles per chain per iteration, then the step's draws.
    PHILOX: the flips of each GROUP of 32 consecutive chain ids (global id >> 5) are one Bernoulli(p) renewal
    process over the interleaved index c = node*32 + lane, window = 32*n positions per iteration: in every round each
-   of the 32 lanes draws one geometric gap from its own stream, event k of the round sits at
+   of the 32 lanes draws one geometric gap from its own PERTURBATION stream (Philox block indices from 2^31 on; the
+   update stream keeps block indices from 0 and is consumed at two words per update), event k of the round sits at
    (last event) + sum of (1+gap) over lanes 0..k, and an event inside the window flips node c>>5 of chain c&31.
    That is the same law as n independent Bernoulli(p) draws per chain per iteration, at ~1 draw per chain.
    bucket = target-node bits MSB-first (pbn_target.py:383-391).  hist is uint64 [2^g], summed over chains. */
@@ -499,9 +500,14 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
 #endif
         uint64_t *h = priv + (int64_t)tid * nb;
         const int64_t gb = gi * 32;
-        Dr d[32];
+        Dr d[32], dp[32]; /* per chain: update stream, and perturbation stream (same key/counter words, block indices from 2^31) */
         uint32_t ev[32], last_p1 = 0;
-        for (int l = 0; l < 32; l++) { dr_init(&d[l], dr, gb + l < chains ? gb + l : 0, env0 + gb + l); ev[l] = NONE; }
+        for (int l = 0; l < 32; l++) {
+            dr_init(&d[l], dr, gb + l < chains ? gb + l : 0, env0 + gb + l);
+            dp[l] = d[l];
+            dp[l].ctr[0] = 0x80000000u;
+            ev[l] = NONE;
+        }
         for (int64_t t = 0; t < iters; t++) {
             for (int l = 0; l < 32 && gb + l < chains; l++) {
                 const uint8_t *st = state + (gb + l) * n;
@@ -524,7 +530,7 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
                         }
                     if (last_p1 > W) break;
                     uint32_t pre = 0;
-                    for (int l = 0; l < 32; l++) { pre += 1u + orc_geom(dr_u32(&d[l]), inv); ev[l] = last_p1 - 1u + pre; }
+                    for (int l = 0; l < 32; l++) { pre += 1u + orc_geom(dr_u32(&dp[l]), inv); ev[l] = last_p1 - 1u + pre; }
                     last_p1 = ev[31] + 1u;
                 }
                 for (int l = 0; l < 32; l++) if (ev[l] != NONE) ev[l] -= W;
