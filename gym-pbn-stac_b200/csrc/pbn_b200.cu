@@ -230,6 +230,10 @@ static DrawView make_draws(const PbnDraws *d) {
     v.seed_lo = (u32)d->seed; v.seed_hi = (u32)(d->seed >> 32);
     v.ints = d->ints; v.dbls = d->dbls;
     v.int_stride = d->int_stride; v.dbl_stride = d->dbl_stride;
+    for (int r = 0; r < 10; r++) {
+        v.rk[2 * r] = v.seed_lo + (u32)r * 0x9E3779B9u;
+        v.rk[2 * r + 1] = v.seed_hi + (u32)r * 0xBB67AE85u;
+    }
     v.used = (long long *)d->used;
     return v;
 }
@@ -695,6 +699,7 @@ struct SsdLoopArgs {
     const NetView &nv;
     const EnvView &ev;
     const SsdParams &sp;
+    const DrawView &dv;
     const unsigned char *blob;
     const int *att_off;
     const u32 *cubes;
@@ -763,6 +768,126 @@ __device__ __forceinline__ void ssd_count(SsdCount &c, const SsdLoopArgs &a, con
     c.run++;
 }
 
+// ---- shared-memory accesses by 32-bit shared-window address (the hot SSD loop keeps its base addresses in registers;
+// through generic pointers ptxas re-derives them from the CTA id in every iteration)
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 lds_u32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_xor_u32(u32 a, u32 v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_add_u32(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 ldc_v4(u32 a) {  // read-only image data: free to schedule
+    uint4 v; asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint2 ldc_v2(u32 a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ u32 keep(u32 x) { asm volatile("" : "+r"(x)); return x; }  // pins a loop invariant in a register
+
+// Loop invariants of the predictor-network SSD loop, as registers.
+struct SsdFast {
+    u32 col;        // shared address of this thread's state column (word w at col + w*1024)
+    u32 warp_cols;  // shared address of lane 0's column of this warp
+    u32 thr, rec;   // shared addresses of the threshold rows / predictor records
+    u32 thr_stride, rec_stride;  // bytes per node
+    u32 shist;      // shared address of the block histogram
+    u32 n, W;
+    u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
+    float inv;
+};
+
+// one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312)
+template <int TQ>
+__device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
+    const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
+    const u32 r = wb >> 1;
+    u32 j = 0;
+#pragma unroll
+    for (int q = 0; q < TQ; q++) {
+        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + q * 16);
+        j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+    }
+    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j * 8u);
+    const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
+    const u32 w0 = lds_u32(f.col + ((p0 & 0xE0u) << 5));
+    const u32 w1 = lds_u32(f.col + ((p1 & 0xE0u) << 5));
+    const u32 w2 = lds_u32(f.col + ((p2 & 0xE0u) << 5));
+    const u32 w3 = lds_u32(f.col + ((p3 & 0xE0u) << 5));
+    u32 idx = __funnelshift_r(w0, 0, p0) & 1u;
+    idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
+    const u32 v = (rec.y >> idx) & 1u;
+    const u32 wa_addr = f.col + ((i & ~31u) << 5);
+    const u32 m = 1u << (i & 31u);
+    const u32 old = lds_u32(wa_addr);
+    sts_u32(wa_addr, (old & ~m) | (v ? m : 0u));
+}
+
+__device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, const DrawView &dv) {
+    for (;;) {
+        if (ps.evp < f.W) {
+            // word (node>>5) of column (evp&31): byte offset = (evp&31)*4 + (node>>5)*1024, node = evp>>5
+            red_xor_u32(f.warp_cols + (((ps.evp << 2) & 0x7Cu) | (ps.evp & 0xFFFFFC00u)), 1u << ((ps.evp >> 5) & 31u));
+            ps.evp = 0xFFFFFFFFu;
+        }
+        if (ps.last_p1 > f.W) break;
+        const u32 pre = warp_scan_add(1u + geom_gap(dp.next_rk(dv), f.inv));
+        ps.evp = ps.last_p1 - 1u + pre;
+        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+    }
+    if (ps.evp != 0xFFFFFFFFu) ps.evp -= f.W;
+    ps.last_p1 -= f.W;
+    __syncwarp();
+}
+
+// STATIC path of predictor networks, full warps, no attractor loop, shared histogram, targets inside one state word:
+// the configuration the headline number is measured in.  Returns the number of iterations done (even).
+template <int TQ>
+__device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const Col &st, Draw<PBN_DRAW_PHILOX> &d,
+                                                    Draw<PBN_DRAW_PHILOX> &dp, SsdPerturb &ps, SsdCount &cnt) {
+    const NetView &nv = a.nv;
+    SsdFast f;
+    f.col = keep(smem_addr(st.s));
+    f.warp_cols = keep(smem_addr(a.sst + (threadIdx.x & ~31u)));
+    f.thr = keep(smem_addr(a.blob + nv.off_thr));
+    f.rec = keep(smem_addr(a.blob + nv.off_rec));
+    f.thr_stride = keep((u32)nv.tsq_stride * 16u);
+    f.rec_stride = keep((u32)nv.fmax * 8u);
+    f.shist = keep(smem_addr(a.shist));
+    f.n = keep((u32)nv.n);
+    f.W = keep((u32)nv.n * 32u);
+    f.b_off = keep(((u32)a.sp.fast_t0 >> 5) << 10);
+    f.b_sh = keep((u32)a.sp.fast_t0 & 31u);
+    f.b_up = keep(32u - (u32)a.sp.g);
+    f.inv = a.sp.inv;
+    u32 ublk = 0;
+    int t = 0;
+    u32 cur = (u32)cnt.cur, run = cnt.run;
+    auto count = [&]() {
+        const u32 b = __brev((lds_u32(f.col + f.b_off) >> f.b_sh) << f.b_up);
+        if (b != cur) {
+            red_add_u32(f.shist + cur * 4u, run);
+            cur = b; run = 0;
+        }
+        run++;
+    };
+    for (; t + 1 < a.iters; t += 2) {
+        u32 x0, x1, x2, x3;
+        philox4x32_10_rk(ublk, d.c1, d.c2, d.c3, a.dv, x0, x1, x2, x3);
+        ublk++;
+        count();
+        ssd_fast_perturb(f, ps, dp, a.dv);
+        ssd_fast_update<TQ>(f, x0, x1);
+        __syncwarp();
+        count();
+        ssd_fast_perturb(f, ps, dp, a.dv);
+        ssd_fast_update<TQ>(f, x2, x3);
+        __syncwarp();
+    }
+    d.blk = ublk;
+    d.have = 0;
+    cnt.cur = (int)cur; cnt.run = run;
+    return t;
+}
+
 template <int NET, int MODE, int TQ, bool HAS_ENV, bool FULL>
 __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Draw<MODE> &d, Draw<MODE> &dp) {
     const NetView &nv = a.nv;
@@ -776,9 +901,12 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
     char *warp_cols = reinterpret_cast<char *>(a.sst + (threadIdx.x & ~31u));
     SsdCount cnt{active ? ssd_bucket(sp, a.s_tgt, st) : 0, 0u};
     int t = 0;
+    if constexpr (MODE == PBN_DRAW_PHILOX && !HAS_ENV && FULL && NET == PBN_NET_PRED && TQ > 0) {
+        if (flips && sp.smem_hist && sp.fast_t0 >= 0) t = ssd_loop_pred_static<TQ>(a, st, d, dp, ps, cnt);
+    }
     if constexpr (MODE == PBN_DRAW_PHILOX && !HAS_ENV && FULL) {
         // STATIC path: one Philox block of the update stream per two iterations, words used in stream order
-        u32 ublk = 0;
+        u32 ublk = d.blk;
         for (; t + 1 < a.iters; t += 2) {
             u32 x0, x1, x2, x3;
             philox4x32_10(ublk, d.c1, d.c2, d.c3, d.k0, d.k1, x0, x1, x2, x3);
@@ -863,7 +991,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
         d.init(dv, e, env0 + e);
         dp.init_perturb(dv, e, env0 + e);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
-        SsdLoopArgs a{nv, ev, sp, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid};
+        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid};
         if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d, dp);   // every lane owns a chain: no predication
         else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d, dp);
         if (active) {

@@ -56,6 +56,9 @@ struct DrawView {
     const double *dbls;
     long long int_stride, dbl_stride;
     long long *used;
+    // Philox round keys (rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85), computed once on the host:
+    // read from the kernel-parameter bank they are immediate operands of the round's XOR instead of ten key updates per block
+    u32 rk[20];
 };
 
 // ----------------------------------------------------------------------------------------------- Philox
@@ -78,6 +81,23 @@ __device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u3
 }
 
 #define PBN_PERTURB_BLOCK0 0x80000000u
+
+// Philox4x32-10 with the round keys taken from the launch's DrawView (a kernel parameter)
+__device__ __forceinline__ void philox4x32_10_rk(u32 c0, u32 c1, u32 c2, u32 c3, const DrawView &dv, u32 &o0, u32 &o1, u32 &o2,
+                                                 u32 &o3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u64 p0 = (u64)0xD2511F53u * c0;
+        u64 p1 = (u64)0xCD9E8D57u * c2;
+        u32 n0 = (u32)(p1 >> 32) ^ c1 ^ dv.rk[2 * r];
+        u32 n2 = (u32)(p0 >> 32) ^ c3 ^ dv.rk[2 * r + 1];
+        c1 = (u32)p1;
+        c3 = (u32)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
 
 template <int MODE>
 struct Draw;
@@ -103,6 +123,17 @@ struct Draw<PBN_DRAW_PHILOX> {
     __device__ __forceinline__ u32 next() {
         if (have == 0) {
             philox4x32_10(blk, c1, c2, c3, k0, k1, b0, b1, b2, b3);
+            blk++;
+            have = 4;
+        }
+        u32 r = b0;
+        b0 = b1; b1 = b2; b2 = b3;
+        have--;
+        return r;
+    }
+    __device__ __forceinline__ u32 next_rk(const DrawView &dv) {  // next() with the host-computed round keys
+        if (have == 0) {
+            philox4x32_10_rk(blk, c1, c2, c3, dv, b0, b1, b2, b3);
             blk++;
             have = 4;
         }
