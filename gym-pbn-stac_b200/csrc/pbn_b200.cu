@@ -224,6 +224,59 @@ __device__ __forceinline__ void store_state(const Col &c, u32 *g, long long B, l
     for (int w = 0; w < w32; w++) g[(long long)w * B + e] = c.word(w);
 }
 
+// ---- shared-memory accesses by 32-bit shared-window address (the hot SSD loop keeps its base addresses in registers;
+// through generic pointers ptxas re-derives them from the CTA id in every iteration)
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 lds_u32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_xor_u32(u32 a, u32 v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_add_u32(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 ldc_v4(u32 a) {  // read-only image data: free to schedule
+    uint4 v; asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint2 ldc_v2(u32 a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ u32 keep(u32 x) { asm volatile("" : "+r"(x)); return x; }  // pins a loop invariant in a register
+
+// Loop invariants of the predictor-network SSD loop, as registers.
+struct SsdFast {
+    u32 col;        // shared address of this thread's state column (word w at col + w*1024)
+    u32 warp_cols;  // shared address of lane 0's column of this warp
+    u32 thr, rec;   // shared addresses of the threshold rows / predictor records
+    u32 thr_stride, rec_stride;  // bytes per node
+    u32 shist;      // shared address of the block histogram
+    u32 n, W;
+    u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
+    float inv;
+};
+
+// one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312)
+template <int TQ>
+__device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
+    const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
+    const u32 r = wb >> 1;
+    u32 j = 0;
+#pragma unroll
+    for (int q = 0; q < TQ; q++) {
+        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + q * 16);
+        j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+    }
+    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j * 8u);
+    const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
+    const u32 w0 = lds_u32(f.col + ((p0 & 0xE0u) << 5));
+    const u32 w1 = lds_u32(f.col + ((p1 & 0xE0u) << 5));
+    const u32 w2 = lds_u32(f.col + ((p2 & 0xE0u) << 5));
+    const u32 w3 = lds_u32(f.col + ((p3 & 0xE0u) << 5));
+    u32 idx = __funnelshift_r(w0, 0, p0) & 1u;
+    idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
+    idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
+    const u32 v = (rec.y >> idx) & 1u;
+    const u32 wa_addr = f.col + ((i & ~31u) << 5);
+    const u32 m = 1u << (i & 31u);
+    const u32 old = lds_u32(wa_addr);
+    sts_u32(wa_addr, (old & ~m) | (v ? m : 0u));
+}
+
 static DrawView make_draws(const PbnDraws *d) {
     DrawView v;
     v.mode = d->mode; v.epoch = d->epoch;
@@ -253,10 +306,40 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
     if (e >= B) return;
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
-    if (sync)
+    if (sync) {
         for (long long t = 0; t < steps; t++) sync_step<NET, MODE, TQ>(nv, blob, st, tmp, d);
-    else
-        for (long long t = 0; t < steps; t++) micro_step<NET, MODE, TQ>(nv, blob, st, d);
+    } else {
+        long long t = 0;
+        if constexpr (MODE == PBN_DRAW_PHILOX) {
+            // an update takes exactly two words of the env's stream: one Philox block per two updates, no buffer bookkeeping
+            u32 ublk = 0;
+            if constexpr (NET == PBN_NET_PRED && TQ > 0) {
+                SsdFast f;
+                f.col = keep(smem_addr(st.s));
+                f.thr = keep(smem_addr(blob + nv.off_thr));
+                f.rec = keep(smem_addr(blob + nv.off_rec));
+                f.thr_stride = keep((u32)nv.tsq_stride * 16u);
+                f.rec_stride = keep((u32)nv.fmax * 8u);
+                f.n = keep((u32)nv.n);
+                for (; t + 1 < steps; t += 2) {
+                    u32 x0, x1, x2, x3;
+                    philox4x32_10_rk(ublk++, d.c1, d.c2, d.c3, dv, x0, x1, x2, x3);
+                    ssd_fast_update<TQ>(f, x0, x1);
+                    ssd_fast_update<TQ>(f, x2, x3);
+                }
+            } else {
+                for (; t + 1 < steps; t += 2) {
+                    u32 x0, x1, x2, x3;
+                    philox4x32_10_rk(ublk++, d.c1, d.c2, d.c3, dv, x0, x1, x2, x3);
+                    micro_step_words<NET, TQ>(nv, blob, st, x0, x1, d);
+                    micro_step_words<NET, TQ>(nv, blob, st, x2, x3, d);
+                }
+            }
+            d.blk = ublk;
+            d.have = 0;
+        }
+        for (; t < steps; t++) micro_step<NET, MODE, TQ>(nv, blob, st, d);
+    }
     store_state(st, state, B, e, nv.w32);
     d.done(dv, e);
 }
@@ -766,59 +849,6 @@ __device__ __forceinline__ void ssd_count(SsdCount &c, const SsdLoopArgs &a, con
         c.cur = b; c.run = 0;
     }
     c.run++;
-}
-
-// ---- shared-memory accesses by 32-bit shared-window address (the hot SSD loop keeps its base addresses in registers;
-// through generic pointers ptxas re-derives them from the CTA id in every iteration)
-__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ u32 lds_u32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_xor_u32(u32 a, u32 v) { asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_add_u32(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint4 ldc_v4(u32 a) {  // read-only image data: free to schedule
-    uint4 v; asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-__device__ __forceinline__ uint2 ldc_v2(u32 a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ u32 keep(u32 x) { asm volatile("" : "+r"(x)); return x; }  // pins a loop invariant in a register
-
-// Loop invariants of the predictor-network SSD loop, as registers.
-struct SsdFast {
-    u32 col;        // shared address of this thread's state column (word w at col + w*1024)
-    u32 warp_cols;  // shared address of lane 0's column of this warp
-    u32 thr, rec;   // shared addresses of the threshold rows / predictor records
-    u32 thr_stride, rec_stride;  // bytes per node
-    u32 shist;      // shared address of the block histogram
-    u32 n, W;
-    u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
-    float inv;
-};
-
-// one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312)
-template <int TQ>
-__device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
-    const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
-    const u32 r = wb >> 1;
-    u32 j = 0;
-#pragma unroll
-    for (int q = 0; q < TQ; q++) {
-        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + q * 16);
-        j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
-    }
-    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j * 8u);
-    const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
-    const u32 w0 = lds_u32(f.col + ((p0 & 0xE0u) << 5));
-    const u32 w1 = lds_u32(f.col + ((p1 & 0xE0u) << 5));
-    const u32 w2 = lds_u32(f.col + ((p2 & 0xE0u) << 5));
-    const u32 w3 = lds_u32(f.col + ((p3 & 0xE0u) << 5));
-    u32 idx = __funnelshift_r(w0, 0, p0) & 1u;
-    idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
-    idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
-    idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
-    const u32 v = (rec.y >> idx) & 1u;
-    const u32 wa_addr = f.col + ((i & ~31u) << 5);
-    const u32 m = 1u << (i & 31u);
-    const u32 old = lds_u32(wa_addr);
-    sts_u32(wa_addr, (old & ~m) | (v ? m : 0u));
 }
 
 __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, const DrawView &dv) {
