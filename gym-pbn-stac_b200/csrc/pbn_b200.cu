@@ -307,7 +307,16 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
     if (sync) {
-        for (long long t = 0; t < steps; t++) sync_step<NET, MODE, TQ>(nv, blob, st, tmp, d);
+        long long t = 0;
+        if constexpr (MODE == PBN_DRAW_PHILOX) {
+            if ((nv.n & 3) == 0) {
+                u32 ublk = 0;
+                for (; t < steps; t++) sync_step_x4<NET, TQ>(nv, dv, blob, st, tmp, d, ublk);
+                d.blk = ublk;
+                d.have = 0;
+            }
+        }
+        for (; t < steps; t++) sync_step<NET, MODE, TQ>(nv, blob, st, tmp, d);
     } else {
         long long t = 0;
         if constexpr (MODE == PBN_DRAW_PHILOX) {

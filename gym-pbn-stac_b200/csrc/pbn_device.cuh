@@ -331,6 +331,24 @@ __device__ __forceinline__ void sync_step(const NetView &nv, const unsigned char
     for (int w = 0; w < nv.w32; w++) st.set_word(w, tmp.word(w));
 }
 
+// The same step when the node count is a multiple of four (Philox mode): node i of step t takes word t*n + i of the
+// env's stream, so every Philox block serves four consecutive nodes and no buffer bookkeeping is needed.
+template <int NET, int TQ = 0>
+__device__ __forceinline__ void sync_step_x4(const NetView &nv, const DrawView &dv, const unsigned char *blob, const Col &st,
+                                             const Col &tmp, Draw<PBN_DRAW_PHILOX> &d, u32 &ublk) {
+    u32 acc = 0;
+    for (int i = 0; i < nv.n; i += 4) {
+        u32 x0, x1, x2, x3;
+        philox4x32_10_rk(ublk++, d.c1, d.c2, d.c3, dv, x0, x1, x2, x3);
+        acc |= node_next<NET, PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, d, x0, true) << (i & 31);
+        acc |= node_next<NET, PBN_DRAW_PHILOX, TQ>(nv, blob, st, i + 1, d, x1, true) << ((i + 1) & 31);
+        acc |= node_next<NET, PBN_DRAW_PHILOX, TQ>(nv, blob, st, i + 2, d, x2, true) << ((i + 2) & 31);
+        acc |= node_next<NET, PBN_DRAW_PHILOX, TQ>(nv, blob, st, i + 3, d, x3, true) << ((i + 3) & 31);
+        if (((i + 3) & 31) == 31 || i + 4 >= nv.n) { tmp.set_word(i >> 5, acc); acc = 0; }
+    }
+    for (int w = 0; w < nv.w32; w++) st.set_word(w, tmp.word(w));
+}
+
 // ----------------------------------------------------------------------------------------------- cubes
 // cubes: u32 [n_cubes][w32][2] = (care, value); a state matches iff (word & care) == value for every word.
 __device__ __forceinline__ bool cube_match(const u32 *cubes, int c, const Col &st, int w32) {

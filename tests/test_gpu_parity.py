@@ -328,6 +328,37 @@ def test_philox_ssd_matches_oracle(eng, which, p):
     assert np.array_equal(_state_np(sim), ost)
 
 
+@pytest.mark.parametrize("which,B,iters,tgt", [
+    ("100_5_kmeans", 64, 1, [0, 1, 2, 3, 4, 5, 6]),       # odd tail only (no static pair)
+    ("100_5_kmeans", 96, 7, [0, 1, 2, 3, 4, 5, 6]),       # three static pairs + one tail iteration
+    ("100_5_kmeans", 64 + 5, 8, [0, 1, 2, 3, 4, 5, 6]),   # last warp not full: generic path next to the static one
+    ("100_5_kmeans", 128, 10, [3, 41, 69, 7]),             # scattered targets: generic bucket, generic static path
+    ("100_5_kmeans", 128, 10, list(range(30, 37))),        # consecutive targets straddling a word boundary
+    ("100_5_kmeans", 128, 10, list(range(40, 53))),        # 13 targets: global-memory histogram
+    ("28_15_median", 160, 9, [20, 21, 22, 23]),            # four threshold quads per node
+    ("200_5_kmeans", 96, 6, [64, 65, 66]),                 # targets in the third state word
+    ("tt", 96, 9, [1, 2, 3]),                              # truth-table network: generic static path
+])
+def test_philox_ssd_loop_variants(eng, which, B, iters, tgt):
+    """Every branch of the SSD loop (static update stream for full warps, specialised predictor path, generic tail)
+    gives the oracle's histogram and final states; the update stream is two words per update, the perturbation gaps
+    come from the env's second Philox stream."""
+    net, onet = _nets(eng, which)
+    seed, tgt = 5, np.array(tgt, np.int32)
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=32)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0), env0=32)
+    hist = sim.ssd(iters, 0.02, tgt)
+    ohist = orc.ssd(onet, None, ost, iters, 0.02, tgt, orc.Draws(seed=seed, epoch=1), env0=32)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
+    assert np.array_equal(_state_np(sim), ost)
+    # a rollout continues from the same states: odd and even step counts of the static update stream
+    for steps in (1, 4, 5):
+        sim.rollout(steps)
+        orc.rollout(onet, ost, steps, orc.Draws(seed=seed, epoch=sim.epoch - 1), env0=32)
+        assert np.array_equal(_state_np(sim), ost), steps
+
+
 def test_philox_ssd_with_attractor_loop(eng):
     net, onet = _nets(eng, "28_15_median")
     rng = np.random.default_rng(8)
