@@ -501,3 +501,43 @@ def test_eval_winrate_matches_single_env_loop():
     assert abs(rate - wins / n) <= 0.5 and abs(inter - np.mean(lens)) <= 2.5
     with pytest.raises(ValueError):
         eval_winrate(env.unwrapped, Policy())  # no step limit anywhere
+
+
+def test_rollout_buffer_and_training_example(monkeypatch, capsys):
+    """Device-resident rollouts over the vector env, and the actor-critic example end to end (two small updates)."""
+    import importlib.util
+    import sys as _sys
+    from pathlib import Path
+
+    import gym_PBN
+    from gym_PBN.b200.rollout import RolloutBuffer
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=32)
+    vec = PBNVectorEnv(env, 256, seed=3)
+    buf = RolloutBuffer(vec, horizon=5, gamma=0.9)
+
+    def policy(obs):
+        a = torch.randint(0, 29, (obs.shape[0], 1), device=obs.device, dtype=torch.int32)
+        return a, None, torch.zeros(obs.shape[0], device=obs.device)
+
+    last = buf.collect(policy)
+    assert buf.t == 5 and buf.obs.shape == (6, 256, 28) and last.shape == (256, 28)
+    assert set(buf.rewards.unique().tolist()) <= {20.0, -5.0}
+    ret = buf.returns()
+    adv, tgt = buf.gae(torch.zeros(256, device=vec.device))
+    assert ret.shape == adv.shape == tgt.shape == (5, 256)
+    assert torch.allclose(ret[-1], buf.rewards[-1])
+    o, a, r, o2, te = buf.transitions()
+    assert o.shape == (5 * 256, 28) and a.shape == (5 * 256, 1) and torch.equal(o2[:256], buf.obs[1])
+
+    path = Path(__file__).resolve().parents[1] / "examples" / "train_vector_policy.py"
+    spec = importlib.util.spec_from_file_location("train_vector_policy", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(_sys, "argv", ["train_vector_policy.py", "--envs", "512", "--updates", "2", "--horizon", "4", "--max-inner", "32"])
+    mod.main()
+    out = capsys.readouterr().out
+    assert "update   1" in out and "env-steps/s" in out

@@ -233,3 +233,27 @@ def test_logic_compiler_agrees_with_python_semantics():
         for vals in itertools.product([False, True], repeat=len(syms)):
             env = dict(zip(syms, vals))
             assert bool(fn(env)) == bool(eval(expr, {"__builtins__": {}}, dict(env))), expr
+
+
+def test_rollout_return_and_gae_math():
+    """gym_PBN.b200.rollout: discounted returns and GAE on torch tensors against plain Python loops (CPU tensors)."""
+    torch = pytest.importorskip("torch")
+    from gym_PBN.b200.rollout import discounted_returns, gae_advantages
+
+    g = torch.Generator().manual_seed(0)
+    T, B, gamma, lam = 9, 5, 0.9, 0.8
+    r = torch.randint(-5, 21, (T, B), generator=g).float()
+    term = torch.rand(T, B, generator=g) < 0.2
+    trunc = (torch.rand(T, B, generator=g) < 0.1) & ~term
+    v = torch.randn(T + 1, B, generator=g)
+    ret = discounted_returns(r, term | trunc, gamma, v[T])
+    adv, target = gae_advantages(r, v, term, trunc, gamma, lam)
+    for b in range(B):
+        run, a = float(v[T, b]), 0.0
+        for t in range(T - 1, -1, -1):
+            done = bool(term[t, b] or trunc[t, b])
+            run = float(r[t, b]) + gamma * run * (not done)
+            assert abs(run - float(ret[t, b])) < 1e-4
+            delta = float(r[t, b]) + gamma * float(v[t + 1, b]) * (not done) - float(v[t, b])
+            a = delta + gamma * lam * (not done) * a
+            assert abs(a - float(adv[t, b])) < 1e-4 and abs(a + float(v[t, b]) - float(target[t, b])) < 1e-4
