@@ -656,6 +656,59 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 // contiguous range of envs and its threads pull the next env from a block-local counter the moment they finish one, in a
 // flat loop whose every trip is "one attractor test + at most one update" for every lane — lanes never wait at the end
 // of an inner loop.  An env's result does not depend on which thread ran it (its Philox stream is keyed by its id).
+// Straggler mode of the step-until-attractor kernel (predictor networks, Philox draws).  When a block's queue is empty and
+// only a few lanes of a warp still hold an env, those envs are finished ONE AT A TIME by the whole warp: the lanes draw 32
+// Philox blocks of the env's update stream at once (64 updates' worth of words, fetched by shuffle), test one attractor cube
+// each, and execute the state-dependent part of the update in lockstep on the env's shared-memory column.  A lone lane in the
+// ordinary loop spends ~1600 cycles per update on a fully dependent instruction chain; here an update is ~200 cycles, which is
+// what bounds a launch whose slowest env needs thousands of updates (the reference's loop is unbounded, pbn_target.py:270-271).
+// The env's words are the same ones the ordinary loop would have used (update k takes words 2k, 2k+1), so results are identical.
+#ifndef PBN_COOP_MAX
+#define PBN_COOP_MAX 2
+#endif
+#ifndef PBN_COOP_MIN_IN
+#define PBN_COOP_MIN_IN 2  // MULTI compares the pre-update observation on its first test; from the second on it is the state
+#endif
+template <int TQ>
+__device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
+                                        const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in) {
+    const u32 lane = threadIdx.x & 31u;
+    const Col st{col_ptr};
+    const int w32 = nv.w32;
+    const int n_cubes = att_off[ev.n_att];
+    Draw<PBN_DRAW_PHILOX> dummy;
+    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    int u = 0, batch = 0;
+    u32 off = 0;
+    for (;;) {
+        bool hit = false;
+        for (int c0 = 0; c0 < n_cubes; c0 += 32) {
+            const int c = c0 + (int)lane;
+            hit |= c < n_cubes && cube_match(cubes, c, st, w32);
+        }
+        if (in >= ev.max_inner || __any_sync(0xFFFFFFFFu, hit)) break;
+        if (u == batch) {  // 32 blocks of the update stream from word 2*in on
+            const u32 a = 2u * (u32)in;
+            off = a & 3u;
+            philox4x32_10_rk((a >> 2) + lane, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
+            u = 0;
+            batch = (int)((128u - off) >> 1);
+        }
+        const u32 w = off + 2u * (u32)u;          // word index inside the batch; (w & 3) is 0 or 2
+        const bool hi_pair = (w & 2u) != 0u;
+        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, w >> 2);
+        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, w >> 2);
+        const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
+        const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
+        __syncwarp();                              // every lane has read the old state
+        if (lane == 0) st.put(i, v);
+        __syncwarp();
+        in++;
+        u++;
+    }
+    return in;
+}
+
 template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
@@ -746,6 +799,28 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
                 if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, const_cast<int *>(target_att), obs_state, B, e, env0, rew, tm, tr, in);
                 have = false;
                 nxt = lo + atomicAdd(&s_next, 1);
+            }
+        }
+        if constexpr (MODE == PBN_DRAW_PHILOX && NET == PBN_NET_PRED) {
+            // straggler mode: few lanes left, nothing more to pull (see coop_run)
+            const unsigned hv = (ev.n_att > 0 && !ev.force) ? __ballot_sync(0xFFFFFFFFu, have && in >= PBN_COOP_MIN_IN) : 0u;
+            if (hv != 0u && __popc(__ballot_sync(0xFFFFFFFFu, have)) <= PBN_COOP_MAX &&
+                lo + *reinterpret_cast<volatile int *>(&s_next) >= hi) {
+                for (unsigned m = hv; m != 0u; m &= m - 1u) {
+                    const int L = __ffs((int)m) - 1;
+                    const long long eL = __shfl_sync(0xFFFFFFFFu, e, L);
+                    const int inL = __shfl_sync(0xFFFFFFFFu, in, L);
+                    u32 *colL = sst + (threadIdx.x & ~31u) + (u32)L;
+                    const int fin = coop_run<TQ>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL);
+                    if ((int)(threadIdx.x & 31u) == L) {
+                        in = fin;
+                        d.blk = (2u * (u32)fin + 3u) >> 2;  // the stream object as the ordinary loop would have left it
+                        d.have = (int)((4u - ((2u * (u32)fin) & 3u)) & 3u);
+                        if (multi)
+                            for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
+                    }
+                }
+                __syncwarp();
             }
         }
     }
