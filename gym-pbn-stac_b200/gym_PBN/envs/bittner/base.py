@@ -81,6 +81,59 @@ class Node:
     def setValue(self, value):
         self.value = value
 
+    # ---- host-side analysis helpers (the reference's STG / attractor side paths; not on the device hot path) -----------
+    def addInputNode(self, inputNode):
+        self.inputNodes = list(getattr(self, "inputNodes", [])) + [inputNode]
+
+    def addInputNodes(self, inputNodes):
+        self.inputNodes = list(getattr(self, "inputNodes", [])) + list(inputNodes)
+
+    def addLUT(self, LUT, inputIDs):
+        self.LUT, self.inputIDs = LUT, inputIDs
+
+    def _table(self):
+        """[(input node indices (3 + self), 16-bit LUT, cumulative COD)] and CODsum of this node, from the compiled network."""
+        if self._graph is None:
+            raise Exception("node is not part of a graph yet (Graph.add_nodes)")
+        a = self._graph.spec.arrays
+        q0, q1 = int(a["pr_off"][self.index]), int(a["pr_off"][self.index + 1])
+        rows = [(a["pr_in"][4 * q:4 * q + 4].tolist(), int(a["pr_lut"][q]), float(a["pr_cum"][q])) for q in range(q0, q1)]
+        return rows, float(a["pr_codsum"][self.index])
+
+    def _output(self, state, inputs, lut):
+        g = self._graph
+        bits = [g._state_bit(state, j) for j in inputs]
+        return (lut >> ((bits[0] << 3) | (bits[1] << 2) | (bits[2] << 1) | bits[3])) & 1
+
+    def getStateProbs(self, state):
+        """[P(next = 0), P(next = 1)] given a state (base.py:66-87): each predictor votes with its COD share."""
+        rows, codsum = self._table()
+        probs, prev = [0, 0], 0.0
+        for inputs, lut, cum in rows:
+            probs[self._output(state, inputs, lut)] += (cum - prev) / codsum
+            prev = cum
+        return probs
+
+    def Predstep(self, state):
+        """One host-side evaluation with a draw from Python's `random`, as base.py:89-119 (the device path does the same
+        with Philox or replayed draws)."""
+        rows, codsum = self._table()
+        r = random.random() * codsum
+        chosen = rows[-1]
+        for row in rows:
+            if row[2] > r:
+                chosen = row
+                break
+        return int(self._output(state, chosen[0], chosen[1]))
+
+    def LUTstep(self, state):
+        raise ValueError("you shouldn't be here")
+
+    def step(self, state, verbose=False):
+        Y = self.LUTstep(state) if self.LUTflag else self.Predstep(state)
+        self.value = Y
+        return Y
+
 
 class Graph:
     def __init__(self, base=2, device=None, seed=None):
@@ -159,9 +212,11 @@ class Graph:
 
     # ---- dynamics ---------------------------------------------------------------------------------------
     def step(self, changed_nodes=None, i=None, steps=1):
-        """Asynchronous update(s) on the device; returns the new state like base.py:306-312."""
+        """Asynchronous update(s) on the device; returns the new state like base.py:306-312.  With a forced node index `i`
+        the single update is evaluated on the host (Node.step, one draw from Python's `random`)."""
         if i is not None:
-            raise NotImplementedError("forcing the updated node index is not supported on the device path")
+            self.nodes[i].step(self.getLabeledState())
+            return self.getState()
         self.sim.rollout(steps)
         return self.getState()
 
@@ -169,6 +224,108 @@ class Graph:
         if self.perturbations:
             raise NotImplementedError("synch_step with perturbations (base.py:287-299) is not on the device path")
         self.sim.rollout(1, sync=True)
+
+    # ---- state-transition analysis (host side; reference: base.py:199-254,398-399) -------------------------
+    def _state_bit(self, state, j):
+        """Value of node index j in `state`: a sequence in node order, or a mapping keyed by gene ID."""
+        if isinstance(state, dict):
+            return int(state[self.nodes[j].ID])
+        return int(state[j])
+
+    def _moves(self, votes_at, start):
+        from collections import defaultdict
+
+        probs = [node.getStateProbs(votes_at) for node in self.nodes]
+        nextStates = defaultdict(float)
+        for i in range(len(start)):
+            nextState = list(start)
+            for v in (0, 1):
+                if probs[i][v] > 0.0:
+                    nextState[i] = v
+                    nextStates[tuple(nextState)] += probs[i][v] / len(start)
+        return nextStates
+
+    def getNextStates(self, state=None):
+        """{next state tuple: probability} of the asynchronous dynamics: node i (chosen w.p. 1/N) takes each value its
+        predictors give with positive probability.  The predictor votes are taken at the graph's CURRENT state, the move
+        starts from `state` (current state when omitted) — as base.py:221-242 does."""
+        cur = tuple(self.getState())
+        return self._moves(cur, cur if state is None else tuple(state))
+
+    def sync_getNextStates(self):
+        """{next state tuple: probability} of the synchronous dynamics (base.py:244-259): product over nodes."""
+        import itertools
+        from collections import defaultdict
+
+        cur = self.getState()
+        probs = [node.getStateProbs(cur) for node in self.nodes]
+        nextStates = defaultdict(float)
+        for state in itertools.product([0, 1], repeat=len(self.nodes)):
+            p = 1
+            for i, v in enumerate(state):
+                p *= probs[i][v]
+            if p > 0:
+                nextStates[state] = p
+        return nextStates
+
+    def genSTG(self, savepath=None):
+        """networkx DiGraph of the asynchronous state-transition graph over all 2^N state tuples (base.py:199-218),
+        including the self-loops the reference adds for values a node can keep.  Host side, for small networks; the
+        attractors of networks up to 32 nodes come from the device search (getAttractors / b200.attractors)."""
+        import itertools
+        import os
+        import pickle
+
+        import networkx as nx
+
+        if savepath is not None and os.path.exists(savepath):
+            with open(savepath, "rb") as f:
+                return pickle.load(f)
+        if self.N > 16:
+            raise ValueError(f"the explicit state-transition graph has 2^{self.N} nodes; use getAttractors (N <= 32) instead")
+        stg = nx.DiGraph()
+        states = list(itertools.product([0, 1], repeat=self.N))
+        stg.add_nodes_from(states)
+        for s in states:
+            for nxt in self._moves(s, s):
+                stg.add_edge(s, nxt)
+        if savepath is not None:
+            with open(savepath, "wb") as f:
+                pickle.dump(stg, f)
+        return stg
+
+    def getAttractors(self, verbal=False):
+        """Attractors (terminal strongly connected components of the asynchronous STG) as lists of state tuples, from the
+        exhaustive device search.  (The reference's method calls an undefined `attractorSetFinder`, base.py:372-374.)"""
+        from gym_PBN.b200 import attractors as _att
+
+        return [sorted(a) for a in _att.attractor_state_sets(self.network)]
+
+    def addEdge(self, startIndex, endIndex):
+        self.nodes[endIndex].addInputNode(self.nodes[startIndex])
+        self.edges = self.edges + [(self.nodes[startIndex], self.nodes[endIndex])]
+
+    def addCon(self, conn):
+        k = conn.shape[0] - 1
+        self.k = k
+        for i in range(conn.shape[1]):
+            targNode = self.getNodeByID(conn[k, i])
+            for j in range(k):
+                predNode = self.getNodeByID(conn[j, i])
+                self.edges = self.edges + [(predNode.index, targNode.index)]
+                targNode.addInputNode(predNode)
+
+    def printGraph(self, path=None, dist=10, charLim=10):
+        """networkx DiGraph of the gene connectivity, node labels = gene names cut to charLim (base.py:341-362)."""
+        import networkx as nx
+
+        self.G = nx.DiGraph()
+        label = lambda node: str(node.name)[:charLim]  # noqa: E731
+        for node in self.nodes:
+            self.G.add_node(label(node))
+            for ID in node.getInputNodes():
+                self.G.add_edge(label(self.getNodeByID(ID)), label(node))
+        return self.G
 
     # ---- descriptive ------------------------------------------------------------------------------------
     def getNames(self):
@@ -182,3 +339,22 @@ class Graph:
             if n.ID == ID:
                 return n
         return None
+
+
+def genBoolList(n, length, b):
+    output = np.zeros((length), dtype=int)
+    for i in range(length):
+        output[i] = n % b
+        n = n // b
+    return output
+
+
+def integerize(state):
+    return sum(int(v) * (2**i) for i, v in enumerate(state))
+
+
+def findAttractors(stg):
+    """Attracting components of a state-transition graph (base.py:398-399)."""
+    import networkx as nx
+
+    return list(nx.attracting_components(stg))

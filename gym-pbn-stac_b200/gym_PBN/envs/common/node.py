@@ -23,5 +23,12 @@ class Node:
             idx = (idx << 1) | int(b)
         return float(self.function.reshape(-1)[idx])
 
+    def compute_next_value(self, state):
+        """Host-side stochastic evaluation with one draw from Python's `random` (common/node.py:34-38); the device step does
+        the same comparison with Philox or replayed draws."""
+        import random
+
+        return random.uniform(0, 1) < self.get_next_value_prob(state)
+
     def __str__(self):
         return f"{self.name}{' (Control)' if self.is_control else ''}"

@@ -41,6 +41,27 @@ class PBCN(PBN):
         else:
             self.sim.rollout(steps)
 
+    @property
+    def control_actions(self):
+        """Every 0/1 vector of length N (common/pbcn.py:114-116 — over N, not M, as there)."""
+        import itertools
+
+        return map(list, itertools.product([0, 1], repeat=self.N))
+
+    def _async_compute_next_states(self, state):
+        """Edge list of the asynchronous STG with the control vector prepended to the target labels' source array, as
+        common/pbcn.py:72-93 builds it (the node probabilities read the plain state)."""
+        state = np.asarray(state, dtype=bool)
+        combined = np.concatenate((self.control_state, state))
+        out = []
+        for i in range(self.N):
+            p = self.nodes[i].get_next_value_prob(state)
+            if (p > 0.0 and not state[i]) or (p < 1.0 and state[i]):
+                nxt = combined.copy()
+                nxt[i] = not state[i]
+                out.append((str(state.astype(int)), str(nxt.astype(int)), p))
+        return out
+
     def reset(self, state=None):
         self.control_state = np.zeros(self.M, dtype=bool)
         return super().reset(state=state)

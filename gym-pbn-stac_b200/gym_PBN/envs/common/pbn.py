@@ -113,6 +113,25 @@ class PBN:
                 out.append((nxt, p))
         return out
 
+    def _compute_next_states(self, state):
+        """[(str(state), str(next state), probability-of-the-node-being-1)] of the asynchronous dynamics, the edge list
+        print_STG feeds to networkx (common/pbn.py:161-197, async_mode branch)."""
+        state = np.asarray(state, dtype=bool)
+        label = str(state.astype(int))
+        return [(label, str(nxt.astype(int)), p) for nxt, p in self.async_successors(state)]
+
+    def _probs_to_states(self, probs):
+        """[(state bool[N], probability)] of the synchronous product law for a (2, N) table of per-node probabilities
+        (common/pbn.py:214-232), zero-probability states left out."""
+        import itertools
+
+        out = []
+        for bits in itertools.product([0, 1], repeat=probs.shape[1]):
+            p = float(np.prod([probs[b, i] for i, b in enumerate(bits)]))
+            if p > 0:
+                out.append((np.array(bits, dtype=bool), p))
+        return out
+
     def print_STG(self, no_cache=False):
         """networkx DiGraph over all 2^N states, node labels = str(int array) as in the reference."""
         import networkx as nx

@@ -33,6 +33,14 @@ class PBCNEnv(PBNEnv):
     def getTargetIdx(self):
         return int(tuple(int(v) for v in self.PBN.state) in self.target_nodes)
 
+    def _get_reward(self, observation):
+        """(reward, terminated, truncated) of an observation, pbcn_env.py:52-65 — the one reward that reads reward_config."""
+        observation_tuple = tuple(int(v) for v in observation)
+        if observation_tuple in self.target_nodes:
+            return self.successful_reward, True, False
+        matched = sum(observation_tuple in attractor for attractor in self.all_attractors)
+        return -self.wrong_attractor_cost * matched, False, False
+
     @staticmethod
     def _flip_index(action):
         a = np.asarray(action).reshape(-1)

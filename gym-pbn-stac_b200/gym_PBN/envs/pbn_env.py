@@ -121,6 +121,22 @@ class PBNEnv(DeviceEnvMixin, Env):
     def set(self, new_state):
         self.PBN.state = np.array(new_state)
 
+    def _get_reward(self, observation, action):
+        """(reward, terminated, truncated) of an observation, pbn_env.py:156-188: +20 and terminated in a target state,
+        else -4 (the state must be attracting, ValueError otherwise) and -1 more for a non-null action."""
+        observation_tuple = tuple(int(v) for v in observation)
+        if observation_tuple in self.target_nodes:
+            return 20, True, False
+        if not self.is_attracting_state(observation):
+            raise ValueError
+        return -4 - (1 if action != 0 else 0), False, False
+
+    def _nx_attractors_to_tuples(self, attractors):
+        return [set(tuple(int(x) for x in state.lstrip("[").rstrip("]").split()) for state in attractor) for attractor in attractors]
+
+    def clip(self, gene_i):
+        self.PBN.clip(gene_i)
+
     def render(self, mode=None):
         mode = self.render_mode if mode is None else mode
         if mode == "human":

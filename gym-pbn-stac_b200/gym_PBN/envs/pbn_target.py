@@ -123,6 +123,56 @@ class PBNTargetEnv(DeviceEnvMixin, Env):
         self.target = target
         self._target_index = self._index_of(target)
 
+    # ---- host-side helpers of the reference class (the device kernel computes the same reward inside env.step) -----
+    def _to_map(self, state):
+        """pbn_target.py:282-287: positional state -> {gene ID: value}."""
+        getIDs = getattr(self.graph, "getIDs", None)
+        if getIDs is not None and type(state) is not dict:
+            state = dict(zip(getIDs(), state))
+        return state
+
+    def _get_reward(self, observation, action):
+        """(reward, terminated, truncated) of an observation, pbn_target.py:303-326: +20 and terminated inside the target
+        attractor, -5 otherwise; truncated at the horizon.  `observation` may be a mapping keyed by gene ID or a sequence."""
+        values = tuple(observation.values()) if hasattr(observation, "values") else tuple(observation)
+        hit = self.in_target(values)
+        return (20, True, self.n_steps == self.horizon) if hit else (-5, False, self.n_steps == self.horizon)
+
+    def compute_attractors(self):
+        """Attractors of the asynchronous dynamics as a list of sets of state tuples (pbn_target.py:393-408, there through
+        an explicit networkx STG; here the exhaustive device search, networks up to 32 genes)."""
+        return att_tools.attractor_state_sets(self.network, list_limit=1 << 22)
+
+    def _nx_attractors_to_tuples(self, attractors):
+        """networkx attracting components over "[0 1 ...]" labels or state tuples -> list of sets of int tuples."""
+        out = []
+        for attractor in attractors:
+            states = set()
+            for state in attractor:
+                if isinstance(state, str):
+                    state = state.lstrip("[").rstrip("]").split()
+                states.add(tuple(int(x) for x in state))
+            out.append(states)
+        return out
+
+    def attractor_checker(self, stg, state, depth):
+        """Depth-limited expansion of the state-transition graph around `state` (pbn_target.py:111-122)."""
+        if depth < 1:
+            return stg
+        stg.add_node(state)
+        next_states = self.graph.getNextStates(state)
+        stg.add_nodes_from(next_states.keys())
+        for ns in next_states:
+            stg.add_edge(state, ns)
+            stg = self.attractor_checker(stg, ns, depth - 1)
+        return stg
+
+    def dep_is_attracting_state(self, state):
+        return True  # the reference's on-line heuristic is disabled by this very line (pbn_target.py:138-139)
+
+    def also_dep_is_attracting_state(self, state):
+        raise ValueError("You are not supposed to be using me")  # pbn_target.py:124-125
+
     def _index_of(self, attractor):
         for i, a in enumerate(self._all_attractors):
             if a is attractor or list(a) == list(attractor):

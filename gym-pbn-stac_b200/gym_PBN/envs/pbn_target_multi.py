@@ -157,6 +157,15 @@ class _BittnerMulti(PBNTargetMultiEnv):
                 self.network, self.target_node_indices, seed=seed or 0)
 
 
+def _statistical_attractors(self, resets=100, steps=1000, top=4):
+    """The `top` most visited states over resets x steps forced updates (pbn_target_multi.py:465-487, there cached in
+    data/attractors_{name}.pkl), sampled on the device."""
+    return [a[0] for a in att_tools.statistical_attractors(self.network, resets, steps, top)]
+
+
+_BittnerMulti.statistical_attractors = _statistical_attractors
+
+
 class BittnerMulti7(_BittnerMulti):
     N = 7
     NAME = "Bittner-7"
@@ -211,6 +220,9 @@ class BittnerMulti100(BittnerMulti70):
 class BittnerMulti200(BittnerMulti70):
     N = 200
     NAME = "Bittner-200"
+
+
+Bittner200 = BittnerMulti200  # the name this class carries in the reference module (pbn_target_multi.py:376)
 
 
 class BittnerMultiGeneral(_BittnerMulti):

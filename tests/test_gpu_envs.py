@@ -541,3 +541,85 @@ def test_rollout_buffer_and_training_example(monkeypatch, capsys):
     mod.main()
     out = capsys.readouterr().out
     assert "update   1" in out and "env-steps/s" in out
+
+
+def test_graph_analysis_helpers_match_reference():
+    """Host-side analysis surface of the Bittner graph (getStateProbs, getNextStates, forced-node step, genSTG,
+    findAttractors, sync_getNextStates) against vectors recorded from the reference (oracle/make_analysis_golden.py)."""
+    import random
+
+    from gym_PBN.envs.bittner import base, utils
+
+    z = load("graph_analysis.npz")
+    g = utils.spawn(total_genes=28, seed=1)
+    for k, s in enumerate(z["b28_states"]):
+        g.setState(list(s))
+        probs = np.array([node.getStateProbs(g.getState()) for node in g.nodes])
+        assert np.allclose(probs, z["b28_probs"][k], rtol=0, atol=1e-12)
+        d = g.getNextStates()
+        lo, hi = z["b28_next_off"][k], z["b28_next_off"][k + 1]
+        assert sorted(d) == [tuple(int(v) for v in r) for r in z["b28_next_states"][lo:hi]]
+        assert np.allclose([d[key] for key in sorted(d)], z["b28_next_probs"][lo:hi], rtol=0, atol=1e-12)
+        assert abs(sum(d.values()) - 1.0) < 1e-9
+    g.setState(list(z["b28_states"][0]))
+    random.seed(5)
+    for k, want in enumerate(z["b28_forced_trace"]):
+        assert list(g.step(i=(7 * k) % 28)) == list(want), k
+    # labelled (ID-keyed) states work too
+    assert g.nodes[3].getStateProbs(g.getLabeledState()) == g.nodes[3].getStateProbs(g.getState())
+
+    n, F = z["s6_cod"].shape
+    nodes = []
+    for i in range(n):
+        buf = np.empty((3, F), dtype=object)
+        for f in range(F):
+            buf[0, f], buf[1, f] = float(z["s6_cod"][i, f]), z["s6_A"][i, f].reshape(4, 1)
+            buf[2, f] = np.array([int(z["s6_ids"][t]) for t in z["s6_inp"][i, f]])
+        node = base.Node(i, i, f"g{i}", int(z["s6_ids"][i]))
+        node.add_predictors(buf)
+        nodes.append(node)
+    g6 = base.Graph(2)
+    g6.add_nodes(nodes)
+    stg = g6.genSTG()
+    assert sorted(u + v for u, v in stg.edges()) == [tuple(int(x) for x in r) for r in z["s6_edges"]]
+    atts = sorted(sorted(a) for a in base.findAttractors(stg))
+    want = [[tuple(int(x) for x in r) for r in z["s6_att_states"][z["s6_att_off"][a]:z["s6_att_off"][a + 1]]]
+            for a in range(len(z["s6_att_off"]) - 1)]
+    assert atts == want
+    assert sorted(sorted(a) for a in g6.getAttractors()) == want  # the exhaustive device search agrees
+    g6.setState([1, 0, 1, 1, 0, 0])
+    d = g6.sync_getNextStates()
+    assert sorted(d) == [tuple(int(x) for x in r) for r in z["s6_sync_states"]]
+    assert np.allclose([d[k] for k in sorted(d)], z["s6_sync_probs"], rtol=0, atol=1e-12)
+    assert g6.printGraph().number_of_nodes() == 6
+
+
+def test_env_reward_helpers():
+    """_get_reward / compute_attractors / _to_map of the env classes give what env.step reports."""
+    import gym_PBN
+
+    env = gym_PBN.make("gym-PBN/PBN-v0", logic_func_data=EX5, goal_config=dict(GOAL)).unwrapped
+    assert env._get_reward((0, 0, 0, 0, 1), 0) == (20, True, False)
+    assert env._get_reward((0, 0, 1, 0, 0), 2) == (-5, False, False)
+    assert env._get_reward((1, 1, 1, 1, 1), 0) == (-4, False, False)  # is_attracting_state is constant True (pbn_env.py:19-21)
+    penv = gym_PBN.make("gym-PBN/PBCN-v0", logic_func_data=EX5, goal_config=dict(GOAL)).unwrapped
+    assert penv._get_reward((0, 0, 0, 0, 1))[:2] == (penv.successful_reward, True)
+    assert penv._get_reward((0, 0, 1, 0, 0))[0] == -penv.wrong_attractor_cost
+    assert len(list(penv.PBN.control_actions)) == 2 ** penv.PBN.N
+    assert penv.PBN._compute_next_states(np.array([0, 0, 1, 0, 0], bool)) == []  # a fixed point: no node can change
+    assert all(len(t) == 3 for t in penv.PBN._async_compute_next_states(np.array([0, 1, 1, 1, 0], bool)))
+    node = env.PBN.nodes[3]
+    assert node.compute_next_value(np.array([0, 1, 0, 0, 0], bool)) in (True, False)
+    assert all(len(t) == 3 for t in env.PBN._compute_next_states(np.array([0, 1, 0, 0, 0], bool)))
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    tenv = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=64, seed=5).unwrapped
+    tenv.reset(seed=3)
+    obs, r, term, trunc, _ = tenv.step(0)
+    assert tenv._get_reward(tenv._to_map(obs), 0)[:2] == (r, term)
+    assert tenv.dep_is_attracting_state(obs) is True
+    with pytest.raises(ValueError):
+        tenv.also_dep_is_attracting_state(obs)
+    found = tenv.compute_attractors()
+    assert sorted(len(a) for a in found) == [120, 49152]  # the two attractors of the 28-gene network (DESIGN.md §7)
