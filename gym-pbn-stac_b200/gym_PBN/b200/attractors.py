@@ -10,8 +10,9 @@ from . import engine
 
 
 def parse_state(text):
-    """CABEAN prints states as space-separated symbols: characters at even positions (get_attractors_from_cabean.py:9-11)."""
-    return tuple(c if c == "*" else int(c) for c in text[::2] if c in "01*")
+    """A state as CABEAN prints it: symbols at the even positions, '-' or '*' = don't care
+    (get_attractors_from_cabean.py:9-11; the full report parser lives in gym_PBN.utils.get_attractors_from_cabean)."""
+    return tuple("*" if c in "-*" else int(c) for c in text[::2])
 
 
 def statistical_attractors(net, resets=100, steps=1000, top=4, care_nodes=None, seed=0):

@@ -112,7 +112,12 @@ def test_compile_cubes():
 def test_parse_cabean_state_format():
     from gym_PBN.b200.attractors import cube_matches, expand_cube, parse_state
 
-    assert parse_state("1 0 1 0 * * 1") == (1, 0, 1, 0, "*", "*", 1)  # sample_cabean_out, get_attractors_from_cabean.py:57-82
+    assert parse_state("1 0 1 0 * * 1") == (1, 0, 1, 0, "*", "*", 1)
+    # the report the reference keeps as its parser fixture (get_attractors_from_cabean.py:57-82)
+    from gym_PBN.utils.get_attractors_from_cabean import parse_attractors, sample_cabean_out
+    assert parse_state("1-0-1-0-----1-") == (1, 0, 1, 0, "*", "*", 1)
+    assert parse_attractors(sample_cabean_out) == {0: [(1, 0, 1, 0, "*", "*", 1)], 1: [(1, 0, 1, 1, 1, 1, 0)],
+                                                   2: [(1, 0, 1, 1, 1, 1, 1)], 3: [(1, 1, 1, 1, 1, 1, 0)]}
     assert len(expand_cube((1, "*", 0, "*"))) == 4 and (1, 1, 0, 0) in expand_cube((1, "*", 0, "*"))
     assert cube_matches((1, "*", 0), (1, 1, 0)) and not cube_matches((1, "*", 0), (0, 1, 0))
 
