@@ -112,3 +112,22 @@ def test_spawn_fit_route_uses_exact_cache_and_reference_node_order():
     shipped = utils.spawn(total_genes=28)
     assert np.array_equal(g.spec.arrays["pr_lut"], shipped.spec.arrays["pr_lut"])
     assert np.array_equal(g.spec.arrays["pr_cum"], shipped.spec.arrays["pr_cum"])
+
+
+def test_inference_example_runs_both_routes(tmp_path):
+    """examples/example_bittner_inference.py (the reference's script of that name): shipped 200-gene set, and a 12-gene
+    median network fitted on the GPU, each followed by the SSD estimate of WNT5A."""
+    import importlib.util
+    from pathlib import Path
+
+    path = Path(__file__).resolve().parents[1] / "examples" / "example_bittner_inference.py"
+    spec = importlib.util.spec_from_file_location("example_bittner_inference", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ssd = mod.main(["--iters", "60000", "--resets", "300"])
+    vals = np.asarray(ssd["Value"])
+    assert vals.shape == (2,) and abs(vals.sum() - 1.0) < 1e-9
+    ssd = mod.main(["--genes", "12", "--method", "median", "--predictors", "3", "--fit", "--iters", "30000", "--resets", "100",
+                    "--cache-dir", str(tmp_path)])
+    assert (tmp_path / "predictor_sets_12_3_median.pkl").exists()
+    assert abs(np.asarray(ssd["Value"]).sum() - 1.0) < 1e-9
