@@ -151,6 +151,11 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL may print its version banner on the C-level stdout at its first collective; the contract is ONE JSON line on
+    # stdout, so file descriptor 1 points at stderr until the warm-up (which runs the first all-reduce) is over
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
@@ -178,6 +183,9 @@ def run_gpu(args):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
 
     # ---- device-resident timing (value): per-step CUDA events, L2 flushed between steps
     sampler = ClockSampler(local)
