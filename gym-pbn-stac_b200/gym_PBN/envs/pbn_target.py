@@ -224,6 +224,10 @@ class PBNTargetEnv(DeviceEnvMixin, Env):
             return self.get_state()
         if mode == "dict":
             return self.graph.getState()
+        if mode == "PBN":
+            return self.graph.printGraph()
+        if mode == "STG":
+            return self.graph.genSTG()  # explicit graph: small networks only (bittner/base.py genSTG)
         if mode == "idx":
             return state_to_idx(self.graph.getState())
         if mode == "float":

@@ -592,6 +592,11 @@ def test_graph_analysis_helpers_match_reference():
     assert sorted(d) == [tuple(int(x) for x in r) for r in z["s6_sync_states"]]
     assert np.allclose([d[k] for k in sorted(d)], z["s6_sync_probs"], rtol=0, atol=1e-12)
     assert g6.printGraph().number_of_nodes() == 6
+    from gym_PBN.envs import PBNTargetEnv
+
+    env6 = PBNTargetEnv(g6, {"target_nodes": [101], "intervene_on": [101], "target_node_values": ((0,),),
+                             "undesired_node_values": tuple(), "horizon": 5}, "human")
+    assert env6.render(mode="STG").number_of_edges() == len(z["s6_edges"]) and env6.render(mode="PBN").number_of_nodes() == 6
 
 
 def test_env_reward_helpers():
