@@ -592,7 +592,6 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int w32 = nv.w32;
     Col st{sst + threadIdx.x};
-    Col ob{sst + w32 * PBN_BLOCK + threadIdx.x};
     if (e < B) load_state(st, state, B, e, w32);
     __syncthreads();
     if (e < B) {
@@ -600,7 +599,6 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     d.init(dv, e, env0 + e);
     const int *act = actions + e * K;
     int rew = 0, tm = 0, tr = 0, in = 0;
-    bool obs_is_state = true;
     switch (ev.kind) {
     case PBN_ENV_PBN: {  // pbn_env.py:141-154, reward :171-183
         int a = act[0];
@@ -639,7 +637,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     default: break;
     }
     store_state(st, state, B, e, w32);
-    if (obs_state) store_state(obs_is_state ? st : ob, obs_state, B, e, w32);
+    if (obs_state) store_state(st, obs_state, B, e, w32);
     reward[e] = rew;
     terminated[e] = (unsigned char)tm;
     truncated[e] = (unsigned char)tr;
@@ -1298,8 +1296,9 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         k_env_step_att<NK, MD, TQ><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
                                                          reward, terminated, truncated, inner_steps, B, env0, per_block, vx); \
     } else {                                                                                                      \
-        if (int rc = set_smem(k_env_step<NK, MD>, smem)) return rc;                                               \
-        k_env_step<NK, MD><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
+        const size_t smem1 = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)nv.w32 * block * 4; /* one column per env */ \
+        if (int rc = set_smem(k_env_step<NK, MD>, smem1)) return rc;                                              \
+        k_env_step<NK, MD><<<grid, block, smem1, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
                                                      reward, terminated, truncated, inner_steps, B, env0, vx);    \
     }
     DISPATCH(nv.kind, dv.mode, att ? nv.ts : 0, CALL);
