@@ -29,6 +29,10 @@ int pbn_fail_(int code, const std::string &msg) { return fail(code, msg); }  // 
 extern "C" const char *pbn_last_error(void) { return g_err.c_str(); }
 extern "C" const char *pbn_version(void) { return "pbn_b200 0.1 (sm_100a)"; }
 
+#ifndef PBN_TT_THR_SMEM_MAX
+#define PBN_TT_THR_SMEM_MAX (16 * 1024)
+#endif
+
 // ----------------------------------------------------------------------------------------------- handles
 struct PbnNet {
     NetView v;
@@ -151,6 +155,14 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
     v.blob_bytes = (int)blob.size();
     rc |= upload(net->owned, blob.data(), blob.size(), &v.blob);
     if (rc) { pbn_net_destroy(net); return PBN_ERR_CUDA; }
+    v.thr_dev = nullptr;
+    if (d->kind == PBN_NET_TT && v.blob_bytes - v.off_thr > PBN_TT_THR_SMEM_MAX) {
+        // Large truth-table networks: the threshold table (4 B per table entry, the last section of the image) stays in
+        // global memory and is read through the L1 (one load per update); only node records and input lists are staged.
+        // With the 32-word state columns of a 1024-node network the image would otherwise limit an SM to two blocks.
+        v.thr_dev = reinterpret_cast<const u32 *>(v.blob + v.off_thr);
+        v.blob_bytes = v.off_thr;
+    }
     if (v.blob_bytes > 160 * 1024) { pbn_net_destroy(net); return fail(PBN_ERR_UNSUPPORTED, "network image exceeds shared memory"); }
     *out = net;
     return PBN_OK;

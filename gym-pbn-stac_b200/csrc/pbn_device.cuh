@@ -30,6 +30,7 @@ struct NetView {
     int blob_bytes;
     int off_thr, off_rec, off_node, off_in;
     const unsigned char *blob;  // device
+    const u32 *thr_dev;         // TT: non-null when the threshold table is read from global memory instead of the staged image
     // float64 side tables for replay mode (device, reference form)
     const int *pr_off;
     const double *pr_cum, *pr_codsum;
@@ -288,7 +289,7 @@ __device__ __forceinline__ u32 tt_next(const NetView &nv, const unsigned char *b
     u32 idx = 0;
     for (int q = 0; q < k; q++) idx = (idx << 1) | st.bit(in[q]);
     if constexpr (MODE == PBN_DRAW_PHILOX) {
-        u32 thr = reinterpret_cast<const u32 *>(blob + nv.off_thr)[nr.x + idx];
+        const u32 thr = nv.thr_dev ? __ldg(nv.thr_dev + nr.x + idx) : reinterpret_cast<const u32 *>(blob + nv.off_thr)[nr.x + idx];
         return (((have_word ? word : d.next()) >> 1) < thr) ? 1u : 0u;
     } else {
         return (d.dbl() < nv.tt_prob[nr.x + idx]) ? 1u : 0u;  // u < p, node.py:37-38
