@@ -1200,7 +1200,8 @@ extern "C" int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double
 // ----------------------------------------------------------------------------------------------- launch glue
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // static + dynamic shared memory above 48 KB needs the opt-in; kernels carry up to 2 KB of static shared memory
+    if (bytes > 46 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PBN_OK;
 }
 static inline int block_for(long long) { return PBN_BLOCK; }  // columns use a compile-time word stride of PBN_BLOCK
