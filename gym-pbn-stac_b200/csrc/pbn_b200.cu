@@ -636,9 +636,18 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     } break;
     case PBN_ENV_PBCN_SD: {  // sampled_data.py:139-189
         int interval = act[0], tstep = -1;
+        // control="write": the control vector goes into nodes 0..M-1 before every update; for M <= 32 that is one masked
+        // store into the first state word instead of M single-bit writes fed by M global loads per update
+        u32 cbits = 0;
+        const u32 cmask = ev.n_control >= 32 ? 0xFFFFFFFFu : ((1u << ev.n_control) - 1u);
+        if (ev.control_write && ev.n_control <= 32)
+            for (int c = 0; c < ev.n_control; c++) cbits |= (act[1 + c] != 0 ? 1u : 0u) << c;
         for (int i = 0; i < interval; i++) {
-            if (ev.control_write)
-                for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
+            if (ev.control_write) {
+                if (ev.n_control <= 32) st.set_word(0, (st.word(0) & ~cmask) | cbits);
+                else
+                    for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
+            }
             micro_step<NET, MODE>(nv, blob, st, d); in++;
             int r = pbcn_reward(ev, att_off, cubes, st, w32, tm) - 1;  // time_step_cost = 1
             if (tstep >= 0) r -= ev.successful_reward;                // overshoot penalty
