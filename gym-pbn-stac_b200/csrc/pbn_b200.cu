@@ -84,7 +84,11 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         }
         const int ts = ((fmax - 1 + 3) / 4) * 4 > 0 ? ((fmax - 1 + 3) / 4) * 4 : 4;
         v.fmax = fmax; v.ts = ts;
-        v.tsq_stride = (ts / 4) | 1;  // odd number of quads per row (bank-conflict padding)
+        // one quad (up to 5 predictors): the row IS the quad.  More: the row starts with a quad holding the LAST threshold
+        // of each threshold quad, so that the search is two 16-byte loads (which quad, then where in it) however many
+        // predictors a node has — divergent 16-byte loads cost four shared-memory wavefronts each
+        const int lead = (ts > 4 && ts <= 16) ? 1 : 0;
+        v.tsq_stride = (lead + ts / 4) | 1;  // odd number of quads per row (bank-conflict padding)
         const int row = v.tsq_stride * 4;
         v.off_thr = 0;
         v.off_rec = n * row * 4;
@@ -93,8 +97,12 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         uint2 *rec = reinterpret_cast<uint2 *>(blob.data() + v.off_rec);
         for (int i = 0; i < n; i++) {
             const int q0 = d->pr_off[i], f = d->pr_off[i + 1] - q0;
-            for (int k = 0; k < row; k++)
-                thr[i * row + k] = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
+            for (int k = 0; k < row; k++) thr[i * row + k] = 0x80000000u;
+            for (int k = 0; k < ts; k++) {
+                const u32 t = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
+                thr[i * row + lead * 4 + k] = t;
+                if (lead && (k & 3) == 3) thr[i * row + (k >> 2)] = t;
+            }
             for (int k = 0; k < fmax; k++) {
                 const int q = q0 + (k < f ? k : f - 1);
                 u32 packed = 0;
@@ -266,11 +274,16 @@ template <int TQ>
 __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
     const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
     const u32 r = wb >> 1;
-    u32 j = 0;
-#pragma unroll
-    for (int q = 0; q < TQ; q++) {
-        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + q * 16);
-        j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+    u32 j;
+    if constexpr (TQ == 1) {
+        const uint4 t = ldc_v4(f.thr + i * f.thr_stride);
+        j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+    } else {  // leading quad = last threshold of each quad (at most four quads when TQ is known)
+        const uint4 m = ldc_v4(f.thr + i * f.thr_stride);
+        u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
+        q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
+        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u);
+        j = 4u * q + (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
     }
     const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j * 8u);
     const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;

@@ -250,11 +250,23 @@ __device__ __forceinline__ u32 pred_next(const NetView &nv, const unsigned char 
         u32 r = (have_word ? word : d.next()) >> 1;
         const int nq = TQ > 0 ? TQ : (nv.ts >> 2);
         const uint4 *thr = reinterpret_cast<const uint4 *>(blob + nv.off_thr) + i * nv.tsq_stride;
-        j = 0;
-#pragma unroll
-        for (int q = 0; q < nq; q++) {
-            uint4 t = thr[q];
-            j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        if (nq == 1) {
+            const uint4 t = thr[0];
+            j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        } else if (nq <= 4) {
+            // rows of two to four quads start with a quad holding the last threshold of each quad (padding = never <= r):
+            // find the quad, then the position inside it — two loads however many predictors the node has
+            const uint4 m = thr[0];
+            int q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
+            q = q < nq - 1 ? q : nq - 1;
+            const uint4 t = thr[1 + q];
+            j = 4 * q + (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        } else {  // more than 17 predictors per node: flat row, linear scan
+            j = 0;
+            for (int q = 0; q < nq; q++) {
+                const uint4 t = thr[q];
+                j += (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+            }
         }
     } else {
         double r = d.dbl() * nv.pr_codsum[i];  // base.py:94

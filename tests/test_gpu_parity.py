@@ -194,6 +194,43 @@ def _nets(eng, which):
     return eng.engine.Network(eng.compiler.load_bittner(which)), orc.net_from_predictor_sets(sets, ids)
 
 
+def _random_predictor_net(eng, n, fmax, seed):
+    """Synthetic predictor sets with 1..fmax predictors per node (the last column of some nodes empty, as add_to_buff leaves it)."""
+    rng = np.random.default_rng(seed)
+    ids = [1000 + 3 * i for i in range(n)]
+    sets = []
+    for i in range(n):
+        f = fmax if i == 0 else int(rng.integers(1, fmax + 1))
+        buf = np.empty((3, fmax), dtype=object)
+        others = [x for x in range(n) if x != i]
+        for k in range(f):
+            trio = rng.choice(others, 3, replace=False)
+            buf[0, k], buf[1, k], buf[2, k] = float(rng.uniform(0.05, 1.0)), rng.normal(size=(4, 1)), np.array([ids[t] for t in trio])
+        sets.append(buf)
+    return eng.engine.Network(eng.compiler.compile_predictor_sets(sets, ids)), orc.net_from_predictor_sets(sets, ids)
+
+
+@pytest.mark.parametrize("fmax", [1, 2, 5, 6, 9, 13, 17, 18, 23])
+def test_threshold_row_layouts(eng, fmax):
+    """Predictor selection for every threshold-row layout: one quad (<= 5 predictors), leading quad + 2..4 quads (6..17),
+    flat rows (more): rollout (async, sync) and SSD against the oracle."""
+    net, onet = _random_predictor_net(eng, 40, fmax, seed=fmax)
+    B, seed = 512, 77
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=64)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0), env0=64)
+    sim.rollout(301)
+    orc.rollout(onet, ost, 301, orc.Draws(seed=seed, epoch=1), env0=64)
+    assert np.array_equal(_state_np(sim), ost)
+    sim.rollout(5, sync=True)
+    orc.rollout(onet, ost, 5, orc.Draws(seed=seed, epoch=2), env0=64, sync=True)
+    assert np.array_equal(_state_np(sim), ost)
+    tgt = np.arange(3, 9, dtype=np.int32)
+    hist = sim.ssd(50, 0.02, tgt)
+    ohist = orc.ssd(onet, None, ost, 50, 0.02, tgt, orc.Draws(seed=seed, epoch=3), env0=64)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist) and np.array_equal(_state_np(sim), ost)
+
+
 @pytest.mark.parametrize("which", ["28_15_median", "100_5_kmeans", "200_5_kmeans", "70_5_kmeans", "tt"])
 @pytest.mark.parametrize("sync", [False, True])
 def test_philox_rollout_matches_oracle(eng, which, sync):
