@@ -1,6 +1,7 @@
-"""GPU probe of the predictor-set fitter: fits the shipped configurations on the device, compares with the shipped
+"""TEST INFRASTRUCTURE (it runs the CPU oracle next to the product, so it lives under tests/).
+GPU probe of the predictor-set fitter: fits the shipped configurations on the device, compares with the shipped
 pickles (reference outputs) and with the CPU oracle on this machine, and prints kernel times.
-  python tools/fit_probe.py [--oracle-genes 4] > gpurun_out/fit_probe.json"""
+  python tests/fit_probe.py [--oracle-genes 4] > gpurun_out/fit_probe.json"""
 import argparse
 import json
 import pickle
