@@ -35,6 +35,14 @@ class DeviceEnvMixin:
     def _invalidate_images(self):
         self._images = {}
 
+    def replay_draws(self, ints, dbls):
+        """Queue recorded draws of the reference's RNGs for the NEXT kernel launch of this env: ints =
+        results of randint / choice, dbls = uniforms, each in the reference's call order.  One entry per launch; launches
+        without a queued entry draw from the env's Philox stream."""
+        if getattr(self, "_replays", None) is None:
+            self._replays = []
+        self._replays.append(engine.Replay(ints, dbls, self.sim.device, B=1))
+
     def _single_io(self, K):
         """Pinned host staging for the single env: actions up, {reward, flags, inner, state, obs} down in ONE read-back."""
         io = getattr(self, "_io", None)
@@ -65,7 +73,9 @@ class DeviceEnvMixin:
         if torch.cuda.current_device() != sim.device.index:
             torch.cuda.set_device(sim.device)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        d = sim._draws()
+        queue = getattr(self, "_replays", None)
+        replay = queue.pop(0) if queue else None
+        d = sim._draws(replay)
         abi.check(lib.pbn_upload(*io["up_args"], stream))
         abi.check(lib.pbn_env_step(*io["step_args"](image, d, stream)))
         abi.check(lib.pbn_fetch_step_host(*io["fetch_args"], stream))

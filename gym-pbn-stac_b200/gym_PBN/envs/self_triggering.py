@@ -18,11 +18,13 @@ from .pbn_env import PBNEnv
 
 class PBNSelfTriggeringEnv(PBNEnv):
     def __init__(self, render_mode="human", render_no_cache=False, PBN_data=None, logic_func_data=None, name=None,
-                 goal_config=None, reward_config=None, gamma=0.99, T=None, device=None, seed=None):
+                 goal_config=None, reward_config=None, gamma=0.99, T=5, device=None, seed=None):
         super().__init__(render_mode, render_no_cache, PBN_data, logic_func_data, name, goal_config, reward_config,
                          device=device, seed=seed)
         self.gamma = gamma
-        self.T = T
+        self.T = T  # default 5 as self_triggering.py:28 (the PBCN variant defaults to None = no cap, :107)
+        # "Reward hardcode" of the reference (:50-53); PBNEnv._get_reward does not read them
+        self.successful_reward, self.wrong_attractor_cost, self.action_cost = 1, 0, 1
         self.primitive_action_space = spaces.Discrete(self.PBN.N + 1)
         self.prob_space = spaces.Discrete(10, start=1)
         self.action_space = spaces.Tuple((self.primitive_action_space, self.prob_space))

@@ -628,3 +628,31 @@ def test_env_reward_helpers():
         tenv.also_dep_is_attracting_state(obs)
     found = tenv.compute_attractors()
     assert sorted(len(a) for a in found) == [120, 49152]  # the two attractors of the 28-gene network
+
+
+@pytest.mark.parametrize("tag", ["pbn", "pbcn"])
+def test_self_triggering_envs_replay_reference(tag, monkeypatch):
+    """PB(C)NSelfTriggeringEnv.step under replayed draws against traces recorded from the reference
+    (oracle/make_st_golden.py): observation, discounted reward (exact float), terminated, interval."""
+    import random
+
+    import gym_PBN
+
+    z = load("ex5_self_triggering.npz")
+    env_id = "gym-PBN/PBN-self-triggering-v0" if tag == "pbn" else "gym-PBN/PBCN-self-triggering-v0"
+    env = gym_PBN.make(env_id, logic_func_data=EX5, goal_config=dict(GOAL), gamma=0.9, T=5 if tag == "pbn" else 7).unwrapped
+    env.reset(seed=1)
+    stops = []
+    monkeypatch.setattr(random, "uniform", lambda a, b: stops.pop(0))
+    for k in range(len(z[f"{tag}_interval"])):
+        n = int(z[f"{tag}_interval"][k])
+        env.set(z[f"{tag}_start"][k].astype(bool))
+        for i in range(n):  # per primitive step: randint -> node, uniform -> node value, then the stop draw
+            env.replay_draws([int(z[f"{tag}_ints"][k][i])], [float(z[f"{tag}_dbls"][k][2 * i])])
+        stops[:] = [float(z[f"{tag}_dbls"][k][2 * i + 1]) for i in range(n)]
+        a0, a1 = (int(v) for v in z[f"{tag}_action"][k])
+        action = (a0, a1) if tag == "pbn" else ([bool(a0)], a1)
+        obs, r, term, trunc, info = env.step(action)
+        assert info["interval"] == n and not stops, k
+        assert np.array_equal(np.asarray(obs).astype(np.uint8), z[f"{tag}_obs"][k]), k
+        assert r == z[f"{tag}_reward"][k] and term == bool(z[f"{tag}_term"][k]), (k, r, z[f"{tag}_reward"][k])
