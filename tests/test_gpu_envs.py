@@ -656,3 +656,58 @@ def test_self_triggering_envs_replay_reference(tag, monkeypatch):
         assert info["interval"] == n and not stops, k
         assert np.array_equal(np.asarray(obs).astype(np.uint8), z[f"{tag}_obs"][k]), k
         assert r == z[f"{tag}_reward"][k] and term == bool(z[f"{tag}_term"][k]), (k, r, z[f"{tag}_reward"][k])
+
+
+def _class_level_replay(env, tr, K, step, on_reset):
+    """Drives an env CLASS through a golden trace of the reference: reset ops restore the recorded state by hand, step ops
+    queue the recorded draws (env.replay_draws) and call env.step."""
+    for t in range(tr.T):
+        ints, dbls = tr.draws(t)
+        if tr.op[t] == 1:
+            on_reset(t)
+            continue
+        env.replay_draws(ints, dbls)
+        obs, r, term, trunc, _info = step(tr.act[t, :K])
+        assert np.array_equal(np.asarray(obs).astype(np.uint8), tr.obs[t]), ("obs", t)
+        assert (int(r), bool(term), bool(trunc)) == (int(tr.reward[t]), bool(tr.term[t]), bool(tr.trunc[t])), ("reward", t)
+
+
+def test_env_classes_replay_reference_traces():
+    """The drop-in env CLASSES (not only the engine) against traces recorded from the reference classes, draws replayed."""
+    from golden_util import Traj, pbn_data_from
+
+    import gym_PBN
+    from gym_PBN.envs import PBNEnv, PBNTargetEnv, PBNTargetMultiEnv
+    from gym_PBN.envs.bittner import utils
+
+    z = load("ex5_pbnenv.npz")
+    env = PBNEnv(logic_func_data=EX5, goal_config=dict(GOAL))
+    for e in range(int(z["n_traj"])):
+        tr = Traj(z, e)
+        _class_level_replay(env, tr, 1, lambda a: env.step(int(a[0])), lambda t: env.set(tr.state[t].astype(bool)))
+
+    for fname, cls, K in (("b28_target_env.npz", PBNTargetEnv, 1), ("b28_multi_env.npz", PBNTargetMultiEnv, 3)):
+        z = load(fname)
+        atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+        goal = {"target_nodes": [234237], "intervene_on": [234237], "target_node_values": ((0,),),
+                "undesired_node_values": tuple(), "horizon": int(z["horizon"])}
+        for e in range(int(z["n_traj"])):
+            if f"e{e}/op" not in z.files:
+                continue
+            tr = Traj(z, e)
+            env = cls(utils.spawn(total_genes=28), dict(goal), "human", all_attractors=atts, max_inner_steps=int(z["cap"]))
+            force = bool(z[f"e{e}/force"]) if f"e{e}/force" in z.files else False
+            as_list = f"e{e}/dedup" in z.files and not bool(z[f"e{e}/dedup"])
+
+            def on_reset(t, env=env, tr=tr):
+                env.graph.setState(list(tr.state[t]))
+                env.n_steps = 0
+                env.setTarget(env._all_attractors[int(tr.target_att[t])])
+
+            def step(a, env=env, force=force, as_list=as_list):
+                if K == 1:
+                    return env.step(int(a[0]), force=force)
+                acts = [int(v) for v in a if v >= 0]
+                return env.step(acts if as_list else torch.tensor(acts))
+
+            _class_level_replay(env, tr, K, step, on_reset)
