@@ -136,10 +136,6 @@ def _candidate(table, g, key):
     return x, table.values[y_row], (ga, gb, gc), y_row
 
 
-class FitStats(dict):
-    pass
-
-
 def _scan(table, rank, top_l, key_gt=None, arr_lt=None, tie_le=None, tie_cap=1 << 16):
     """One device scan -> (sorted non-tie keys per gene, [(key_with_best_case_rank, gene)], kernel ms)."""
     G = len(table.genes)
@@ -182,7 +178,7 @@ def fit_predictor_sets(table, n_predictors=5, stats=None):
     if n_predictors < 2 or n_predictors > 17:
         raise ValueError("n_predictors must be in 2..17")
     L = n_predictors - 1
-    cod, rank = _rank_tables(table)
+    _cod, rank = _rank_tables(table)
     ms_total, n_settled = 0.0, 0
 
     def best_with_ties(top_l, key_gt=None, arr_lt=None, exclude=None):
