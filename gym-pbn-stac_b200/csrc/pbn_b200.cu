@@ -186,7 +186,10 @@ extern "C" int pbn_net_words(const PbnNet *net) { return net ? net->v.w32 : 0; }
 
 extern "C" int pbn_env_create(const PbnNet *net, const PbnEnvDesc *d, PbnEnv **out) {
     if (!net || !d || !out) return fail(PBN_ERR_ARG, "null argument");
-    if (d->kind < PBN_ENV_PBN || d->kind > PBN_ENV_PBCN_SD) return fail(PBN_ERR_ARG, "unknown env kind");
+    if (d->kind < PBN_ENV_PBN || d->kind > PBN_ENV_PBCN_ST) return fail(PBN_ERR_ARG, "unknown env kind");
+    const bool self_trig = d->kind == PBN_ENV_PBN_ST || d->kind == PBN_ENV_PBCN_ST;
+    if (self_trig && (!d->gamma_pow || d->n_gamma < 1 || d->max_interval < 0))
+        return fail(PBN_ERR_ARG, "self-triggering envs need the gamma**i table and T >= 0");
     const int n = net->v.n, w32 = net->v.w32;
     PbnEnv *env = new PbnEnv();
     env->net = net;
@@ -219,6 +222,10 @@ extern "C" int pbn_env_create(const PbnNet *net, const PbnEnvDesc *d, PbnEnv **o
     v.img_bytes = (int)img.size();
     if (v.img_bytes + net->v.blob_bytes > 190 * 1024) { delete env; return fail(PBN_ERR_UNSUPPORTED, "cube tables exceed shared memory"); }
     if (upload(env->owned, img.data(), img.size(), &v.img)) { pbn_env_destroy(env); return PBN_ERR_CUDA; }
+    if (self_trig) {
+        v.n_gamma = d->n_gamma; v.max_interval = d->max_interval;
+        if (upload(env->owned, d->gamma_pow, (size_t)d->n_gamma, &v.gamma_pow)) { pbn_env_destroy(env); return PBN_ERR_CUDA; }
+    }
     *out = env;
     return PBN_OK;
 }
@@ -604,7 +611,7 @@ template <int NET, int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
                                                         int *reward, unsigned char *terminated, unsigned char *truncated,
-                                                        int *inner_steps, long long B, long long env0, VecView vx) {
+                                                        int *inner_steps, long long B, long long env0, VecView vx, double *rew_f64) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
@@ -667,6 +674,46 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
             else if (tm) tstep = i;
             rew += r;
         }
+    } break;
+    case PBN_ENV_PBN_ST:     // self_triggering.py:56-93: (action, prob 1..10)
+    case PBN_ENV_PBCN_ST: {  // self_triggering.py:146-197: (prob 1..10, control bits...)
+        const bool pbcn = ev.kind == PBN_ENV_PBCN_ST;
+        const int a = pbcn ? 0 : act[0];
+        const double prob = (double)act[pbcn ? 0 : 1] / 10.0;  // convert value in [1,10] to [0.1 .. 1]
+        const u32 stop_thr = (u32)ceil(prob * 2147483648.0);   // Philox: stop iff r31 < ceil(prob * 2^31)
+        u32 cbits = 0;
+        const u32 cmask = ev.n_control >= 32 ? 0xFFFFFFFFu : ((1u << ev.n_control) - 1u);
+        if (pbcn && ev.control_write && ev.n_control <= 32)
+            for (int c = 0; c < ev.n_control; c++) cbits |= (act[1 + c] != 0 ? 1u : 0u) << c;
+        double total = 0.0;
+        int i = 0;
+        bool end = false;
+        while (!end) {
+            int r;
+            if (!pbcn) {
+                if (a != 0) st.flip(a - 1);
+                micro_step<NET, MODE>(nv, blob, st, d);
+                if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { r = 20; tm = 1; }
+                else { r = -4 - (a != 0); tm = 0; }
+            } else {
+                if (ev.control_write) {
+                    if (ev.n_control <= 32) st.set_word(0, (st.word(0) & ~cmask) | cbits);
+                    else
+                        for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
+                }
+                micro_step<NET, MODE>(nv, blob, st, d);
+                r = pbcn_reward(ev, att_off, cubes, st, w32, tm) - 1;  // time step cost
+            }
+            total += ev.gamma_pow[i < ev.n_gamma ? i : ev.n_gamma - 1] * (double)r;  // total_reward += gamma**i * reward
+            i++;
+            bool stop;
+            if constexpr (MODE == PBN_DRAW_PHILOX) stop = (d.next() >> 1) < stop_thr;
+            else stop = d.dbl() <= prob;  // random.uniform(0, 1) <= prob
+            end = stop || i == ev.max_interval;
+        }
+        in = i;
+        rew = (int)total;
+        if (rew_f64) rew_f64[e] = total;
     } break;
     default: break;
     }
@@ -1285,8 +1332,15 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
 static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
                          const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
                          uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
-                         const PbnVecState *vec, void *stream) {
+                         const PbnVecState *vec, void *stream, double *reward_f64 = nullptr) {
     if (!env || !state || !actions || !reward || !terminated || !truncated || B < 0 || K < 1) return fail(PBN_ERR_ARG, "bad argument");
+    {
+        const int kd = env->v.kind;
+        if ((kd == PBN_ENV_PBN_ST || kd == PBN_ENV_PBCN_ST) && !reward_f64)
+            return fail(PBN_ERR_ARG, "self-triggering envs return a float64 reward: call pbn_env_step_f64");
+        if ((kd == PBN_ENV_PBN_ST && K != 2) || (kd == PBN_ENV_PBCN_ST && K != 1 + env->v.n_control))
+            return fail(PBN_ERR_ARG, "wrong action width for this env kind");
+    }
     if ((env->v.kind == PBN_ENV_TARGET || env->v.kind == PBN_ENV_MULTI) && (!n_steps || !target_att))
         return fail(PBN_ERR_ARG, "target envs need n_steps and target_att");
     if ((env->v.kind == PBN_ENV_PBN_SD && K != 2) || (env->v.kind == PBN_ENV_PBCN_SD && K != 1 + env->v.n_control))
@@ -1334,7 +1388,7 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         const size_t smem1 = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)nv.w32 * block * 4; /* one column per env */ \
         if (int rc = set_smem(k_env_step<NK, MD>, smem1)) return rc;                                              \
         k_env_step<NK, MD><<<grid, block, smem1, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                     reward, terminated, truncated, inner_steps, B, env0, vx);    \
+                                                     reward, terminated, truncated, inner_steps, B, env0, vx, reward_f64); \
     }
     DISPATCH(nv.kind, dv.mode, att ? nv.ts : 0, CALL);
 #undef CALL
@@ -1348,6 +1402,15 @@ extern "C" int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
                             void *stream) {
     return env_step_impl(env, state, n_steps, target_att, actions, K, obs_state, reward, terminated, truncated, inner_steps, B,
                          env0, draws, nullptr, stream);
+}
+
+extern "C" int pbn_env_step_f64(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                                const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, double *reward_f64,
+                                uint8_t *terminated, uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0,
+                                const PbnDraws *draws, void *stream) {
+    if (!reward_f64) return fail(PBN_ERR_ARG, "reward_f64 is null");
+    return env_step_impl(env, state, n_steps, target_att, actions, K, obs_state, reward, terminated, truncated, inner_steps, B,
+                         env0, draws, nullptr, stream, reward_f64);
 }
 
 extern "C" int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,

@@ -47,6 +47,8 @@ struct EnvView {
     int img_bytes;               // bytes of [att_off (n_att+1 ints, padded to 8)] [cubes: n_cubes*w32*2 u32]
     int off_cubes;
     const unsigned char *img;    // device
+    const double *gamma_pow;     // device, self-triggering envs: gamma**i for i < n_gamma
+    int n_gamma, max_interval;
 };
 
 struct DrawView {

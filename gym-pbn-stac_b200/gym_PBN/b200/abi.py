@@ -11,7 +11,7 @@ PKG_ROOT = Path(__file__).resolve().parents[2]  # gym-pbn-stac_b200/
 LIB_PATH = Path(os.environ.get("PBN_B200_LIB", PKG_ROOT / "lib" / "libpbn_b200.so"))  # override = kernel experiments only
 
 NET_TT, NET_PRED = 0, 1
-ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD = range(6)
+ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD, ENV_PBN_ST, ENV_PBCN_ST = range(8)
 DRAW_PHILOX, DRAW_REPLAY = 0, 1
 
 
@@ -27,7 +27,8 @@ class PbnEnvDesc(C.Structure):
                 ("dedup", C.c_int32), ("control_write", C.c_int32), ("n_control", C.c_int32),
                 ("successful_reward", C.c_int32), ("wrong_attractor_cost", C.c_int32),
                 ("n_att", C.c_int32), ("att_off", C.c_void_p), ("cube", C.c_void_p),
-                ("tgt_first", C.c_int32), ("n_tgt", C.c_int32)]
+                ("tgt_first", C.c_int32), ("n_tgt", C.c_int32),
+                ("gamma_pow", C.c_void_p), ("n_gamma", C.c_int32), ("max_interval", C.c_int32)]
 
 
 class PbnDraws(C.Structure):
@@ -58,6 +59,9 @@ EXPORTS = {
     "pbn_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_env_step_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_vec_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PbnVecState), C.c_int64, C.c_int64,
                                C.POINTER(PbnDraws), C.c_void_p]),

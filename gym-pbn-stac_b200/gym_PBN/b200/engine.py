@@ -65,7 +65,8 @@ class EnvImage:
     """Compiled env description (cubes, rewards, horizon) bound to a Network."""
 
     def __init__(self, net: Network, kind, attractors=(), targets=(), horizon=100, max_inner=1 << 20, force=False,
-                 dedup=True, control_write=False, n_control=0, successful_reward=10, wrong_attractor_cost=2):
+                 dedup=True, control_write=False, n_control=0, successful_reward=10, wrong_attractor_cost=2,
+                 gamma=None, max_interval=None):
         self.net, self.kind = net, kind
         self.n_att = len(attractors)
         cube, off, tgt_first, n_tgt = compile_cubes(net.n, attractors, targets)
@@ -74,6 +75,12 @@ class EnvImage:
                            dedup=int(bool(dedup)), control_write=int(bool(control_write)), n_control=int(n_control),
                            successful_reward=int(successful_reward), wrong_attractor_cost=int(wrong_attractor_cost),
                            n_att=self.n_att, att_off=_np_ptr(off), cube=_np_ptr(cube), tgt_first=tgt_first, n_tgt=n_tgt)
+        if kind in (abi.ENV_PBN_ST, abi.ENV_PBCN_ST):
+            # gamma**i exactly as the reference computes it (Python float pow, self_triggering.py:76,178); the kernel only
+            # multiplies and adds.  With no cap (T = None) the interval is geometric with p >= 0.1: 2048 entries are plenty.
+            n_gamma = int(max_interval) if max_interval else 2048
+            self._gamma_pow = np.array([float(gamma) ** i for i in range(n_gamma)], np.float64)
+            d.gamma_pow, d.n_gamma, d.max_interval = _np_ptr(self._gamma_pow), n_gamma, int(max_interval or 0)
         h = C.c_void_p()
         with torch.cuda.device(net.device):
             abi.check(abi.lib().pbn_env_create(net.handle, C.byref(d), C.byref(h)))
@@ -185,6 +192,16 @@ class Simulator:
         obs_state (overwritten by the next call)."""
         actions = actions.to(self.device, dtype=torch.int32).reshape(self.B, -1).contiguous()
         d = self._draws(replay)
+        if env.kind in (abi.ENV_PBN_ST, abi.ENV_PBCN_ST):  # discounted float64 reward (self.reward_f64), interval in self.inner
+            if getattr(self, "reward_f64", None) is None:
+                self.reward_f64 = torch.zeros(self.B, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                abi.check(abi.lib().pbn_env_step_f64(
+                    env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att), _ptr(actions), actions.shape[1],
+                    _ptr(self.obs_state), _ptr(self.reward), _ptr(self.reward_f64), _ptr(self.terminated), _ptr(self.truncated),
+                    _ptr(self.inner), self.B, self.env0, C.byref(d), _stream()))
+                self.launches += 1
+            return
         with torch.cuda.device(self.device):
             abi.check(abi.lib().pbn_env_step(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
                                              _ptr(actions), actions.shape[1], _ptr(self.obs_state), _ptr(self.reward),

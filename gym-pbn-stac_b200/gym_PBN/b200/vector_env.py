@@ -24,7 +24,9 @@ def _family(env):
     from gym_PBN.envs.pbn_target_multi import PBNTargetMultiEnv
 
     if "SelfTriggering" in type(env).__name__:
-        raise TypeError("self-triggering envs draw their interval per step on the host (self_triggering.py:79,181) and are not vectorised")
+        raise TypeError("self-triggering envs return float64 discounted rewards; step them in batches with engine.Simulator.env_step "
+                        "(env kinds ENV_PBN_ST / ENV_PBCN_ST, results in sim.reward_f64 / sim.inner) — the fused vector step keeps "
+                        "integer episode returns")
     if isinstance(env, PBNTargetMultiEnv):
         return "multi"
     if isinstance(env, PBNTargetEnv):

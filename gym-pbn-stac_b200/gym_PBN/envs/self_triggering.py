@@ -1,11 +1,12 @@
 """Self-triggering envs (reference: gym_PBN/envs/self_triggering.py): a macro action is (primitive, prob in 1..10);
 after every primitive step it stops with probability prob/10 (or at i == T), inner rewards are discounted by gamma**i.
-SURVEY.md §8f ranks these "next"; they are served by looping the single-step kernel from the host, with the stop draw
-taken from Python's `random.uniform` exactly where the reference draws it (self_triggering.py:79,181).
+The whole macro step is ONE kernel launch (env kinds PBN_ENV_PBN_ST / PBN_ENV_PBCN_ST of pbn_env_step_f64): per primitive
+step the draws are node index, node value, stop — the reference's order (self_triggering.py:64-80,165-181) — and the
+discounted sum is accumulated in float64 from a gamma**i table computed by Python's own pow, so that under replayed draws
+the reward equals the reference's bit for bit (tests/test_gpu_envs.py, tests/test_oracle_golden.py).
 """
-import random
-
 import numpy as np
+import torch
 
 from gym_PBN.b200 import abi, engine
 from gym_PBN.b200.gym_compat import spaces
@@ -14,6 +15,17 @@ from gym_PBN.utils import booleanize
 from ._device import state_to_idx
 from .pbcn_env import PBCNEnv
 from .pbn_env import PBNEnv
+
+
+def _macro_step(env, image, acts):
+    """One launch of the self-triggering kernel for the single env -> (discounted reward, terminated, truncated, interval)."""
+    queue = getattr(env, "_replays", None)
+    replay = queue.pop(0) if queue else None
+    sim = env.sim
+    sim.env_step(image, torch.tensor([acts], dtype=torch.int32), replay=replay)
+    out = (float(sim.reward_f64[0]), bool(sim.terminated[0]), bool(sim.truncated[0]), int(sim.inner[0]))
+    env._last_state = sim.unpack()[0].cpu().numpy()
+    return out
 
 
 class PBNSelfTriggeringEnv(PBNEnv):
@@ -30,22 +42,16 @@ class PBNSelfTriggeringEnv(PBNEnv):
         self.action_space = spaces.Tuple((self.primitive_action_space, self.prob_space))
         self.discrete_action_space = spaces.Discrete(self.primitive_action_space.n * self.prob_space.n)
 
-    def _one_step_image(self):  # PBNSampledDataEnv's body with interval = 1: flip(a-1), update, PBNEnv reward
-        return self._image("st1", lambda: engine.EnvImage(
-            self.network, abi.ENV_PBN_SD, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states()))
+    def _st_image(self):
+        return self._image(("st", self.gamma, self.T), lambda: engine.EnvImage(
+            self.network, abi.ENV_PBN_ST, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states(),
+            gamma=self.gamma, max_interval=self.T))
 
     def step(self, action):
         if not self.action_space.contains(action):
             raise Exception(f"Invalid action {action}, not in action space.")
         control_action, prob = action
-        prob = prob / 10
-        total_reward, i, end = 0, 0, False
-        terminated = truncated = False
-        while not end:
-            reward, terminated, truncated, _ = self._run_step(self._one_step_image(), [int(control_action), 1])
-            total_reward += (self.gamma**i) * reward
-            i += 1
-            end = random.uniform(0, 1) <= prob or i == self.T
+        total_reward, terminated, truncated, i = _macro_step(self, self._st_image(), [int(control_action), int(prob)])
         observation = self._last_state.astype(bool)
         return observation, total_reward, terminated, truncated, {
             "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}
@@ -73,11 +79,12 @@ class PBCNSelfTriggeringEnv(PBCNEnv):
         m = self.PBN.M
         return booleanize(i % (2**m), m).tolist(), i // (2**m) + 1
 
-    def _one_step_image(self):  # PBCNSampledDataEnv's body with interval = 1: reward - 1 (time step cost)
-        return self._image("st1", lambda: engine.EnvImage(
-            self.network, abi.ENV_PBCN_SD, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states(),
+    def _st_image(self):
+        return self._image(("st", self.gamma, self.T), lambda: engine.EnvImage(
+            self.network, abi.ENV_PBCN_ST, attractors=[sorted(a) for a in self.all_attractors], targets=self._target_states(),
             n_control=self.PBN.M, control_write=self.PBN.control_mode == "write",
-            successful_reward=self.successful_reward, wrong_attractor_cost=self.wrong_attractor_cost))
+            successful_reward=self.successful_reward, wrong_attractor_cost=self.wrong_attractor_cost,
+            gamma=self.gamma, max_interval=self.T))
 
     def step(self, action):
         if action is None:
@@ -91,16 +98,9 @@ class PBCNSelfTriggeringEnv(PBCNEnv):
         if not self.action_space.contains(action):
             raise Exception(f"Invalid action {action}, not in action space.")
         control_action, prob = action
-        prob = prob / 10
         control = [int(bool(c)) for c in np.asarray(control_action).reshape(-1)]
         self.PBN.apply_control(control)
-        total_reward, i, end = 0, 0, False
-        terminated = truncated = False
-        while not end:
-            reward, terminated, truncated, _ = self._run_step(self._one_step_image(), [1] + control)
-            total_reward += (self.gamma**i) * reward
-            i += 1
-            end = random.uniform(0, 1) <= prob or i == self.T
+        total_reward, terminated, truncated, i = _macro_step(self, self._st_image(), [int(prob)] + control)
         observation = self._last_state.astype(bool)
         return observation, total_reward, terminated, truncated, {
             "control_action": control_action, "interval": i, "observation_idx": state_to_idx(observation), "T": self.T}

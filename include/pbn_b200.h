@@ -70,6 +70,8 @@ int pbn_net_words(const PbnNet *net); /* W32 */
 #define PBN_ENV_MULTI 3   /* PBNTargetMultiEnv  pbn_target_multi.py:119-225 */
 #define PBN_ENV_PBN_SD 4  /* PBNSampledDataEnv  sampled_data.py:52-88 */
 #define PBN_ENV_PBCN_SD 5 /* PBCNSampledDataEnv sampled_data.py:139-189 */
+#define PBN_ENV_PBN_ST 6  /* PBNSelfTriggeringEnv  self_triggering.py:56-93 */
+#define PBN_ENV_PBCN_ST 7 /* PBCNSelfTriggeringEnv self_triggering.py:146-197 */
 
 typedef struct {
     int32_t kind;
@@ -86,6 +88,11 @@ typedef struct {
     const int32_t *att_off;
     const int8_t *cube;
     int32_t tgt_first, n_tgt; /* PBN family: the target set = cubes tgt_first .. tgt_first+n_tgt (full states) */
+    /* self-triggering envs: gamma_pow[i] = gamma**i as the HOST computes it (Python float pow; the device only multiplies
+       and adds), i < n_gamma (later steps reuse the last entry); max_interval = T, 0 = no cap (self_triggering.py:75-80) */
+    const double *gamma_pow;
+    int32_t n_gamma;
+    int32_t max_interval;
 } PbnEnvDesc;
 
 typedef struct PbnEnv PbnEnv;
@@ -116,11 +123,20 @@ int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, int
 
 /* K2 — one env.step for B envs: intervention -> update(s) until attracting (cap) -> reward/terminated/truncated.
    actions [B][K]: PBN/PBCN/TARGET K=1; MULTI K slots (<0 = absent); PBN_SD (action, interval);
-   PBCN_SD (interval, control bits...).  obs_state (optional) receives the packed observation planes (differs from
+   PBCN_SD (interval, control bits...); PBN_ST / PBCN_ST need pbn_env_step_f64.  obs_state (optional) receives the packed observation planes (differs from
    `state` only for MULTI's pre-update capture, pbn_target_multi.py:133-135). */
 int pbn_env_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
                  const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
                  uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* The same call for the self-triggering envs (PBN_ENV_PBN_ST / PBN_ENV_PBCN_ST), whose reward is the discounted sum of the
+   inner rewards, a float64 (self_triggering.py:76,178): actions (action, prob 1..10) resp. (prob 1..10, control bits...);
+   after every primitive step the macro action stops w.p. prob/10 or at T; reward_f64 [B] receives the sum, `reward` its
+   truncation to int, inner_steps the interval.  Draws per primitive step: node index, node value, stop. */
+int pbn_env_step_f64(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
+                     const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, double *reward_f64,
+                     uint8_t *terminated, uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0,
+                     const PbnDraws *draws, void *stream);
 
 /* Vector-env step: K2 plus, in the same launch, the bookkeeping a batched env needs — running episode return/length,
    block-aggregated statistics (episodes, return sum, length sum, successes, inner-cap hits, env steps; accumulated into

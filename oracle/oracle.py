@@ -20,7 +20,7 @@ LIB = BUILD / "libpbn_oracle.so"
 
 ORC_TT, ORC_PRED = 0, 1
 PHILOX, REPLAY = 0, 1
-ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD = range(6)
+ENV_PBN, ENV_PBCN, ENV_TARGET, ENV_MULTI, ENV_PBN_SD, ENV_PBCN_SD, ENV_PBN_ST, ENV_PBCN_ST = range(8)
 
 
 def build(force=False):
@@ -52,7 +52,8 @@ class OrcEnv(C.Structure):
                 ("dedup", C.c_int32), ("control_write", C.c_int32), ("n_control", C.c_int32),
                 ("successful_reward", C.c_int32), ("wrong_attractor_cost", C.c_int32),
                 ("n_att", C.c_int32), ("att_off", C.c_void_p), ("cube", C.c_void_p),
-                ("tgt_first", C.c_int32), ("n_tgt", C.c_int32)]
+                ("tgt_first", C.c_int32), ("n_tgt", C.c_int32),
+                ("gamma_pow", C.c_void_p), ("n_gamma", C.c_int32), ("max_interval", C.c_int32)]
 
 
 _lib = None
@@ -148,8 +149,9 @@ def net_from_predictor_sets(sets, node_ids):
 
 class Env:
     def __init__(self, kind, n, attractors=(), targets=(), horizon=100, max_inner=1 << 30, force=0, dedup=1,
-                 control_write=0, n_control=0, successful_reward=10, wrong_attractor_cost=2):
-        """attractors: list of lists of cubes (tuples over 0/1/'*'); targets: list of full states (PBN family)."""
+                 control_write=0, n_control=0, successful_reward=10, wrong_attractor_cost=2, gamma=None, max_interval=None):
+        """attractors: list of lists of cubes (tuples over 0/1/'*'); targets: list of full states (PBN family);
+        gamma / max_interval: self-triggering envs (gamma**i tabulated here with Python's float pow, as the reference does)."""
         cubes, off = [], [0]
         for att in attractors:
             for cube in att:
@@ -164,6 +166,10 @@ class Env:
                         control_write=control_write, n_control=n_control, successful_reward=successful_reward,
                         wrong_attractor_cost=wrong_attractor_cost, n_att=len(off) - 1, att_off=_p(self.att_off),
                         cube=_p(self.cube), tgt_first=tgt_first, n_tgt=len(targets))
+        if gamma is not None:
+            n_gamma = int(max_interval) if max_interval else 2048
+            self.gamma_pow = np.array([float(gamma) ** i for i in range(n_gamma)], np.float64)
+            self.c.gamma_pow, self.c.n_gamma, self.c.max_interval = _p(self.gamma_pow), n_gamma, int(max_interval or 0)
 
 
 class Draws:
@@ -214,6 +220,20 @@ def env_step(net, env, state, n_steps, target_att, actions, draws, env0=0):
                        C.c_int(actions.shape[1]), _p(obs), _p(reward), _p(term), _p(trunc), _p(inner),
                        C.c_int64(B), C.c_int64(env0), C.byref(draws.c))
     return obs, reward, term, trunc, inner
+
+
+def env_step_f64(net, env, state, actions, draws, env0=0):
+    """Self-triggering envs: -> (obs, discounted reward float64, terminated, interval)."""
+    B = state.shape[0]
+    actions = np.ascontiguousarray(actions, np.int32).reshape(B, -1)
+    obs = np.zeros_like(state)
+    reward, rf = np.zeros(B, np.int32), np.zeros(B, np.float64)
+    term, trunc, inner = np.zeros(B, np.uint8), np.zeros(B, np.uint8), np.zeros(B, np.int32)
+    ns, ta = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    lib().orc_env_step_f64(C.byref(net.c), C.byref(env.c), _p(state), _p(ns), _p(ta), _p(actions), C.c_int(actions.shape[1]),
+                           _p(obs), _p(reward), _p(rf), _p(term), _p(trunc), _p(inner), C.c_int64(B), C.c_int64(env0),
+                           C.byref(draws.c))
+    return obs, rf, term, inner
 
 
 def env_reset(net, env, state, n_steps, target_att, draws, mask=None, target_state=None, env0=0):

@@ -64,6 +64,8 @@ typedef struct {
 #define ORC_ENV_MULTI 3    /* PBNTargetMultiEnv   pbn_target_multi.py:119-225 */
 #define ORC_ENV_PBN_SD 4   /* PBNSampledDataEnv   sampled_data.py:52-88 */
 #define ORC_ENV_PBCN_SD 5  /* PBCNSampledDataEnv  sampled_data.py:139-189 */
+#define ORC_ENV_PBN_ST 6   /* PBNSelfTriggeringEnv  self_triggering.py:56-93 */
+#define ORC_ENV_PBCN_ST 7  /* PBCNSelfTriggeringEnv self_triggering.py:146-197 */
 
 typedef struct {
     int32_t kind, horizon, max_inner;
@@ -78,6 +80,9 @@ typedef struct {
     const int8_t *cube;
     /* PBN/PBCN target set = full states, tgt_off = first cube of the target list, n_tgt entries (pbn_env.py:55-59) */
     int32_t tgt_first, n_tgt;
+    /* self-triggering envs: gamma_pow[i] = gamma**i as Python computes it, i < n_gamma; max_interval = T (0 = no cap) */
+    const double *gamma_pow;
+    int32_t n_gamma, max_interval;
 } OrcEnv;
 
 /* ------------------------------------------------------------------------------------ Philox4x32-10 */
@@ -332,9 +337,9 @@ static inline int pbcn_reward(const OrcEnv *env, const uint8_t *st, int n, int *
    PBN_SD: K=2 (primitive action, interval).  PBCN_SD: K = 1 + n_control (interval, control bits).
    outputs: reward int32[B], term/trunc uint8[B], inner int32[B] (micro-steps executed), obs uint8[B][n]
    (obs differs from state only for MULTI's pre-update capture, Q11). */
-int orc_env_step(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, const int32_t *target_att,
-                 const int32_t *actions, int K, uint8_t *obs, int32_t *reward, uint8_t *term, uint8_t *trunc,
-                 int32_t *inner, int64_t B, int64_t env0, const OrcDraws *dr) {
+static int env_step_impl(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, const int32_t *target_att,
+                         const int32_t *actions, int K, uint8_t *obs, int32_t *reward, uint8_t *term, uint8_t *trunc,
+                         int32_t *inner, int64_t B, int64_t env0, const OrcDraws *dr, double *reward_f64) {
     const int n = net->n;
 #pragma omp parallel for schedule(dynamic, 64) if (B >= 256)
     for (int64_t e = 0; e < B; e++) {
@@ -405,12 +410,51 @@ int orc_env_step(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *
             }
             memcpy(ob, st, (size_t)n);
         } break;
+        case ORC_ENV_PBN_ST:    /* self_triggering.py:56-93: (action, prob 1..10) */
+        case ORC_ENV_PBCN_ST: { /* self_triggering.py:146-197: (prob 1..10, control bits...) */
+            const int pbcn = env->kind == ORC_ENV_PBCN_ST;
+            const int a = pbcn ? 0 : act[0];
+            const double prob = (double)act[pbcn ? 0 : 1] / 10.0; /* prob /= 10 */
+            const uint32_t stop_thr = (uint32_t)ceil(prob * 2147483648.0);
+            double total = 0.0;
+            int i = 0, end = 0;
+            while (!end) {
+                int r;
+                if (!pbcn) {
+                    if (a != 0) st[a - 1] ^= 1;
+                    micro_step(net, st, &d);
+                    if (in_target_set(env, st, n)) { r = 20; tm = 1; } else { r = -4 - (a != 0); tm = 0; } /* PBNEnv._get_reward */
+                } else {
+                    if (env->control_write) for (int c = 0; c < env->n_control; c++) st[c] = (uint8_t)(act[1 + c] != 0);
+                    micro_step(net, st, &d);
+                    r = pbcn_reward(env, st, n, &tm) - 1; /* time step cost */
+                }
+                total += env->gamma_pow[i < env->n_gamma ? i : env->n_gamma - 1] * (double)r; /* total += gamma**i * reward */
+                i++;
+                int stop = d.mode == ORC_REPLAY ? (dr_dbl(&d) <= prob) : ((dr_u32(&d) >> 1) < stop_thr);
+                end = stop || i == env->max_interval; /* random.uniform(0, 1) <= prob or i == T */
+            }
+            in = i;
+            rew = (int)total;
+            if (reward_f64) reward_f64[e] = total;
+            memcpy(ob, st, (size_t)n);
+        } break;
         default: break;
         }
         reward[e] = rew; term[e] = (uint8_t)tm; trunc[e] = (uint8_t)tr; inner[e] = in;
         dr_done(&d, dr, e);
     }
     return 0;
+}
+int orc_env_step(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, const int32_t *target_att,
+                 const int32_t *actions, int K, uint8_t *obs, int32_t *reward, uint8_t *term, uint8_t *trunc,
+                 int32_t *inner, int64_t B, int64_t env0, const OrcDraws *dr) {
+    return env_step_impl(net, env, state, n_steps, target_att, actions, K, obs, reward, term, trunc, inner, B, env0, dr, NULL);
+}
+int orc_env_step_f64(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, const int32_t *target_att,
+                     const int32_t *actions, int K, uint8_t *obs, int32_t *reward, double *reward_f64, uint8_t *term,
+                     uint8_t *trunc, int32_t *inner, int64_t B, int64_t env0, const OrcDraws *dr) {
+    return env_step_impl(net, env, state, n_steps, target_att, actions, K, obs, reward, term, trunc, inner, B, env0, dr, reward_f64);
 }
 
 /* reset for the envs selected by mask (NULL = all).

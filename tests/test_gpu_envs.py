@@ -631,31 +631,52 @@ def test_env_reward_helpers():
 
 
 @pytest.mark.parametrize("tag", ["pbn", "pbcn"])
-def test_self_triggering_envs_replay_reference(tag, monkeypatch):
-    """PB(C)NSelfTriggeringEnv.step under replayed draws against traces recorded from the reference
-    (oracle/make_st_golden.py): observation, discounted reward (exact float), terminated, interval."""
-    import random
-
+def test_self_triggering_envs_replay_reference(tag):
+    """PB(C)NSelfTriggeringEnv.step (one kernel launch per macro step) under replayed draws against traces recorded from
+    the reference (oracle/make_st_golden.py): observation, discounted reward (exact float64), terminated, interval; and the
+    same kernel in Philox mode against the oracle."""
     import gym_PBN
+    from gym_PBN.b200 import abi, engine
 
     z = load("ex5_self_triggering.npz")
+    T = 5 if tag == "pbn" else 7
     env_id = "gym-PBN/PBN-self-triggering-v0" if tag == "pbn" else "gym-PBN/PBCN-self-triggering-v0"
-    env = gym_PBN.make(env_id, logic_func_data=EX5, goal_config=dict(GOAL), gamma=0.9, T=5 if tag == "pbn" else 7).unwrapped
+    env = gym_PBN.make(env_id, logic_func_data=EX5, goal_config=dict(GOAL), gamma=0.9, T=T).unwrapped
     env.reset(seed=1)
-    stops = []
-    monkeypatch.setattr(random, "uniform", lambda a, b: stops.pop(0))
     for k in range(len(z[f"{tag}_interval"])):
         n = int(z[f"{tag}_interval"][k])
         env.set(z[f"{tag}_start"][k].astype(bool))
-        for i in range(n):  # per primitive step: randint -> node, uniform -> node value, then the stop draw
-            env.replay_draws([int(z[f"{tag}_ints"][k][i])], [float(z[f"{tag}_dbls"][k][2 * i])])
-        stops[:] = [float(z[f"{tag}_dbls"][k][2 * i + 1]) for i in range(n)]
+        env.replay_draws(z[f"{tag}_ints"][k][:n], z[f"{tag}_dbls"][k][:2 * n])  # per primitive step: node, value, stop
         a0, a1 = (int(v) for v in z[f"{tag}_action"][k])
-        action = (a0, a1) if tag == "pbn" else ([bool(a0)], a1)
-        obs, r, term, trunc, info = env.step(action)
-        assert info["interval"] == n and not stops, k
+        obs, r, term, trunc, info = env.step((a0, a1) if tag == "pbn" else ([bool(a0)], a1))
+        assert info["interval"] == n, k
         assert np.array_equal(np.asarray(obs).astype(np.uint8), z[f"{tag}_obs"][k]), k
         assert r == z[f"{tag}_reward"][k] and term == bool(z[f"{tag}_term"][k]), (k, r, z[f"{tag}_reward"][k])
+
+    # Philox mode, many envs: kernel == oracle (float64 rewards bit for bit)
+    B, seed = 777, 21
+    rng = np.random.default_rng(4)
+    kind, okind = (abi.ENV_PBN_ST, orc.ENV_PBN_ST) if tag == "pbn" else (abi.ENV_PBCN_ST, orc.ENV_PBCN_ST)
+    atts = [[(0, 0, 1, 0, 0)], [(0, 0, 0, 0, 1)]]
+    common = dict(attractors=atts, targets=[(0, 0, 0, 0, 1)], n_control=1, successful_reward=1, wrong_attractor_cost=1,
+                  gamma=0.97, max_interval=T)
+    img = engine.EnvImage(env.network, kind, **common)
+    oenv = orc.Env(okind, 5, **common)
+    from gym_PBN.utils.converters import logic_funcs_to_PBN_data
+
+    onet = orc.net_from_pbn_data(logic_funcs_to_PBN_data(*EX5))
+    sim = engine.Simulator(env.network, B, seed=seed)
+    st0 = rng.integers(0, 2, size=(B, 5)).astype(np.uint8)
+    sim.set_state(st0)
+    ost = st0.copy()
+    for t in range(3):
+        act = (np.stack([rng.integers(0, 6, B), rng.integers(1, 11, B)], 1) if tag == "pbn"
+               else np.stack([rng.integers(1, 11, B), rng.integers(0, 2, B)], 1)).astype(np.int32)
+        sim.env_step(img, torch.from_numpy(act))
+        obs, rf, term, inner = orc.env_step_f64(onet, oenv, ost, act, orc.Draws(seed=seed, epoch=sim.epoch - 1))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost), t
+        assert np.array_equal(sim.reward_f64.cpu().numpy(), rf) and np.array_equal(sim.inner.cpu().numpy(), inner), t
+        assert np.array_equal(sim.terminated.cpu().numpy(), term), t
 
 
 def _class_level_replay(env, tr, K, step, on_reset):

@@ -165,3 +165,27 @@ def test_ssd_policy_branch_b28():
         d = _rd(z["ints"][z["int_off"][t]:z["int_off"][t + 1]], z["dbls"][z["dbl_off"][t]:z["dbl_off"][t + 1]])
         orc.env_step(net, env, st, n_steps, tatt, np.array([[a]], np.int32), d)
     assert np.array_equal(hist, z["hist"]) and np.array_equal(st[0], z["final"])
+
+
+@pytest.mark.parametrize("tag", ["pbn", "pbcn"])
+def test_oracle_self_triggering_envs(tag):
+    """orc_env_step_f64 (PB(C)NSelfTriggeringEnv.step) against traces recorded from the reference
+    (oracle/make_st_golden.py): observation, discounted float64 reward bit for bit, terminated, interval, draws consumed."""
+    z = load("ex5_self_triggering.npz")
+    ex5 = load("ex5_pbnenv.npz")
+    pbn_data = [(m, t, f"n{i}", False) for i, (m, t) in enumerate(pbn_data_from(ex5))]
+    net = orc.net_from_pbn_data(pbn_data)
+    atts = [[(0, 0, 1, 0, 0)], [(0, 0, 0, 0, 1)]]
+    kind = orc.ENV_PBN_ST if tag == "pbn" else orc.ENV_PBCN_ST
+    env = orc.Env(kind, 5, attractors=atts, targets=[(0, 0, 0, 0, 1)], n_control=1, successful_reward=1, wrong_attractor_cost=1,
+                  gamma=0.9, max_interval=5 if tag == "pbn" else 7)
+    for k in range(len(z[f"{tag}_interval"])):
+        n = int(z[f"{tag}_interval"][k])
+        st = z[f"{tag}_start"][k:k + 1].copy()
+        a0, a1 = (int(v) for v in z[f"{tag}_action"][k])
+        act = [a0, a1] if tag == "pbn" else [a1, a0]
+        d = orc.Draws(ints=z[f"{tag}_ints"][k:k + 1, :n], dbls=z[f"{tag}_dbls"][k:k + 1, :2 * n])
+        obs, rf, term, inner = orc.env_step_f64(net, env, st, np.array([act], np.int32), d)
+        assert int(inner[0]) == n and tuple(d.used[0]) == (n, 2 * n), k
+        assert np.array_equal(obs[0], z[f"{tag}_obs"][k]) and bool(term[0]) == bool(z[f"{tag}_term"][k]), k
+        assert rf[0] == z[f"{tag}_reward"][k], (k, rf[0], z[f"{tag}_reward"][k])
