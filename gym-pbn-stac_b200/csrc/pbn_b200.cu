@@ -1230,6 +1230,31 @@ __global__ void __launch_bounds__(256) k_peak_alu(long long iters, u32 *sink) {
     }
     if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) sink[0] = a0;
 }
+// single-opcode variants (inline PTX so that ptxas cannot trade one opcode for another): which pipe an opcode class issues on,
+// and at what rate, decides how far a given instruction MIX can get towards one instruction per cycle per scheduler
+template <int OP>  // 0 = LOP3, 1 = SHF (funnel shift), 2 = IMAD (mad.lo), 3 = IADD3
+__global__ void __launch_bounds__(256) k_peak_op(long long iters, u32 *sink) {
+    u32 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * (2 * i + 3) + i;
+    const u32 k = blockIdx.x | 1, k2 = (blockIdx.x << 3) | 5;
+    for (long long t = 0; t < iters; t++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {  // 8 independent chains x 16 = 128 ops / iteration
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (OP == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(k), "r"(k2));
+                else if (OP == 1) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k), "r"(k2));
+                else if (OP == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k), "r"(k2));
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(k));
+            }
+        }
+    }
+    u32 x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a[i];
+    if (x == 0x12345678u) sink[0] = x;
+}
 __global__ void __launch_bounds__(256) k_peak_philox(long long iters, u32 *sink) {
     u32 acc = 0, o0, o1, o2, o3;
     const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1253,13 +1278,18 @@ extern "C" int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double
     for (int rep = 0; rep < 2; rep++) {  // first pass warms up
         CK(cudaEventRecord(a));
         if (kind == 0) k_peak_alu<<<grid, block>>>(iters, sink);
-        else k_peak_philox<<<grid, block>>>(iters, sink);
+        else if (kind == 1) k_peak_philox<<<grid, block>>>(iters, sink);
+        else if (kind == 2) k_peak_op<0><<<grid, block>>>(iters, sink);
+        else if (kind == 3) k_peak_op<1><<<grid, block>>>(iters, sink);
+        else if (kind == 4) k_peak_op<2><<<grid, block>>>(iters, sink);
+        else if (kind == 5) k_peak_op<3><<<grid, block>>>(iters, sink);
+        else return fail(PBN_ERR_ARG, "pbn_issue_peak: kind must be 0..5");
         CK(cudaEventRecord(b));
         CK(cudaEventSynchronize(b));
     }
     CK(cudaGetLastError());
     CK(cudaEventElapsedTime(ms_out, a, b));
-    *ops_out = (double)grid * block * (double)iters * (kind == 0 ? 128.0 : 1.0);
+    *ops_out = (double)grid * block * (double)iters * (kind == 1 ? 1.0 : 128.0);
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(sink);

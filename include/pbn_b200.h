@@ -245,8 +245,8 @@ int pbn_fetch_step_host(const int32_t *reward, const uint8_t *terminated, const 
                         void *scratch_dev, void *dst_host, void *stream);
 
 /* instruction-issue microbenchmarks used by bench.py for the roofline denominator:
-   kind 0 = dependent-free LOP3/IADD3 chain, kind 1 = Philox4x32-10 blocks.  Writes elapsed ms and the number of
-   thread-level operations executed. */
+   kind 0 = dependent-free LOP3/IADD3 chain, kind 1 = Philox4x32-10 blocks, kinds 2..5 = one opcode only (LOP3, SHF, IMAD,
+   IADD) to see the issue rate of each class.  Writes elapsed ms and the number of thread-level operations executed. */
 int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double *ops_out);
 
 const char *pbn_last_error(void);
