@@ -779,9 +779,8 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
         const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, w >> 2);
         const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
         const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
-        __syncwarp();                              // every lane has read the old state
-        if (lane == 0) st.put(i, v);
-        __syncwarp();
+        st.put(i, v);  // every lane writes the same word with the same value and later reads back at least its own write:
+                       // no warp barrier is needed on the critical path
         in++;
         u++;
     }
