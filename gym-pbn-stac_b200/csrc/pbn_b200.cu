@@ -743,15 +743,30 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 // what bounds a launch whose slowest env needs thousands of updates (the reference's loop is unbounded, pbn_target.py:270-271).
 // The env's words are the same ones the ordinary loop would have used (update k takes words 2k, 2k+1), so results are identical.
 #ifndef PBN_COOP_MAX
-#define PBN_COOP_MAX 2
+#define PBN_COOP_MAX 8   // live envs per warp at which straggler mode takes over (groups of 32 / 8 = 4 lanes)
+#endif
+// In a small batch (at most PBN_COOP_SMALL_BATCH envs per block, i.e. one or two per thread) the launch is as long as its
+// slowest env and the SMs are mostly idle, so the mode starts early; in a large batch the SM is issue-bound and a warp
+// switches only for its last two envs.
+#ifndef PBN_COOP_SMALL_BATCH
+#define PBN_COOP_SMALL_BATCH 512
 #endif
 #ifndef PBN_COOP_MIN_IN
 #define PBN_COOP_MIN_IN 2  // MULTI compares the pre-update observation on its first test; from the second on it is the state
 #endif
-template <int TQ>
+// The warp is split into k = 1, 2, 4 or 8 groups of g = 32 / k lanes; group r finishes the env of the r-th live lane, all
+// groups at once.  Inside a group the lanes draw g Philox blocks of the env's update stream in one go (2g updates' worth of
+// words, fetched by shuffle), share out the attractor cubes, and execute the state-dependent part of the update in lockstep
+// on the env's shared-memory column (every lane of the group writes the same word with the same value and reads back at
+// least its own write, so no barrier sits on the critical path).  Returns the group's final update count.
+template <int TQ, int G>  // G = 32: the whole warp on one env (group size known at compile time); G = 0: run-time group size g
 __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
-                                        const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in) {
+                                        const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
+                                        bool active, int g_rt) {
+    const int g = G > 0 ? G : g_rt;
     const u32 lane = threadIdx.x & 31u;
+    const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
+    const u32 gmask = (g == 32 ? 0xFFFFFFFFu : ((1u << g) - 1u)) << gbase;
     const Col st{col_ptr};
     const int w32 = nv.w32;
     const int n_cubes = att_off[ev.n_att];
@@ -759,30 +774,36 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
     u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
     int u = 0, batch = 0;
     u32 off = 0;
+    bool running = active;
     for (;;) {
         bool hit = false;
-        for (int c0 = 0; c0 < n_cubes; c0 += 32) {
-            const int c = c0 + (int)lane;
-            hit |= c < n_cubes && cube_match(cubes, c, st, w32);
-        }
-        if (in >= ev.max_inner || __any_sync(0xFFFFFFFFu, hit)) break;
-        if (u == batch) {  // 32 blocks of the update stream from word 2*in on
+        if (running)
+            for (int c0 = 0; c0 < n_cubes; c0 += g) {
+                const int c = c0 + (int)sub;
+                hit |= c < n_cubes && cube_match(cubes, c, st, w32);
+            }
+        const unsigned votes = __ballot_sync(0xFFFFFFFFu, hit);
+        if (running && (in >= ev.max_inner || (votes & gmask) != 0u)) running = false;
+        if (!__any_sync(0xFFFFFFFFu, running)) break;
+        if (running && u == batch) {  // g blocks of the update stream from word 2*in on (uniform inside a group)
             const u32 a = 2u * (u32)in;
             off = a & 3u;
-            philox4x32_10_rk((a >> 2) + lane, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
+            philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
             u = 0;
-            batch = (int)((128u - off) >> 1);
+            batch = (int)((4u * (u32)g - off) >> 1);
         }
         const u32 w = off + 2u * (u32)u;          // word index inside the batch; (w & 3) is 0 or 2
         const bool hi_pair = (w & 2u) != 0u;
-        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, w >> 2);
-        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, w >> 2);
-        const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
-        const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
-        st.put(i, v);  // every lane writes the same word with the same value and later reads back at least its own write:
-                       // no warp barrier is needed on the critical path
-        in++;
-        u++;
+        const u32 src = gbase + ((w >> 2) & (u32)(g - 1));
+        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, src);
+        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, src);
+        if (running) {
+            const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
+            const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
+            st.put(i, v);
+            in++;
+            u++;
+        }
     }
     return in;
 }
@@ -882,21 +903,41 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
         if constexpr (MODE == PBN_DRAW_PHILOX && NET == PBN_NET_PRED) {
             // straggler mode: few lanes left, nothing more to pull (see coop_run)
             const unsigned hv = (ev.n_att > 0 && !ev.force) ? __ballot_sync(0xFFFFFFFFu, have && in >= PBN_COOP_MIN_IN) : 0u;
-            if (hv != 0u && __popc(__ballot_sync(0xFFFFFFFFu, have)) <= PBN_COOP_MAX &&
+            if (hv != 0u && __popc(__ballot_sync(0xFFFFFFFFu, have)) <= (per_block <= PBN_COOP_SMALL_BATCH ? PBN_COOP_MAX : 2) &&
                 lo + *reinterpret_cast<volatile int *>(&s_next) >= hi) {
-                for (unsigned m = hv; m != 0u; m &= m - 1u) {
-                    const int L = __ffs((int)m) - 1;
-                    const long long eL = __shfl_sync(0xFFFFFFFFu, e, L);
-                    const int inL = __shfl_sync(0xFFFFFFFFu, in, L);
-                    u32 *colL = sst + (threadIdx.x & ~31u) + (u32)L;
-                    const int fin = coop_run<TQ>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL);
-                    if ((int)(threadIdx.x & 31u) == L) {
-                        in = fin;
-                        d.blk = (2u * (u32)fin + 3u) >> 2;  // the stream object as the ordinary loop would have left it
-                        d.have = (int)((4u - ((2u * (u32)fin) & 3u)) & 3u);
+                const u32 lane = threadIdx.x & 31u;
+                auto take_back = [&](int owner_lane, int v) {  // the env's owner resumes with the count the group reached
+                    if ((int)lane == owner_lane && v != in) {
+                        in = v;
+                        d.blk = (2u * (u32)v + 3u) >> 2;  // the stream object as the ordinary loop would have left it
+                        d.have = (int)((4u - ((2u * (u32)v) & 3u)) & 3u);
                         if (multi)
                             for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
                     }
+                };
+                if (per_block > PBN_COOP_SMALL_BATCH) {
+                    // busy SM: the last one or two envs of the warp, one after the other, the whole warp on each
+                    for (unsigned m = hv; m != 0u; m &= m - 1u) {
+                        const int L = __ffs((int)m) - 1;
+                        const long long eL = __shfl_sync(0xFFFFFFFFu, e, L);
+                        const int inL = __shfl_sync(0xFFFFFFFFu, in, L);
+                        u32 *colL = sst + (threadIdx.x & ~31u) + (u32)L;
+                        take_back(L, coop_run<TQ, 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32));
+                    }
+                } else {
+                    const int nl = __popc(hv);
+                    int k = 1;
+                    while (k < nl) k <<= 1;                 // groups: 1, 2, 4 or 8
+                    const int g = 32 / k;                   // lanes per group
+                    const int grp = (int)lane / g;
+                    const bool active = grp < nl;
+                    const int owner = active ? (int)__fns(hv, 0u, grp + 1) : 0;  // the grp-th live lane
+                    const long long eL = __shfl_sync(0xFFFFFFFFu, e, owner);
+                    const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
+                    u32 *colL = sst + (threadIdx.x & ~31u) + (u32)owner;
+                    const int fin = coop_run<TQ, 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g);
+                    for (int r = 0; r < nl; r++)            // hand each group's count back to the lane that owns the env
+                        take_back((int)__fns(hv, 0u, r + 1), __shfl_sync(0xFFFFFFFFu, fin, r * g));
                 }
                 __syncwarp();
             }
