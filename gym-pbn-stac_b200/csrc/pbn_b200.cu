@@ -909,7 +909,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
                 auto take_back = [&](int owner_lane, int v) {  // the env's owner resumes with the count the group reached
                     if ((int)lane == owner_lane && v != in) {
                         in = v;
-                        d.blk = (2u * (u32)v + 3u) >> 2;  // the stream object as the ordinary loop would have left it
+                        // coop_run returns only when the env is attracting or capped, so no word is drawn from `d` again:
+                        // only its position (what d.done reports) is brought up to date, not its buffered words
+                        d.blk = (2u * (u32)v + 3u) >> 2;
                         d.have = (int)((4u - ((2u * (u32)v) & 3u)) & 3u);
                         if (multi)
                             for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
