@@ -967,6 +967,7 @@ struct SsdParams {
     int g;
     int smem_hist;  // 1: per-block shared histogram (g <= 12), 0: global atomics
     int fast_t0;    // >= 0: the targets are nodes t0, t0+1, .. t0+g-1 inside one state word (bucket = bit-reversed field)
+    int win;        // iterations per window of the step-until-attractor path (0 = iteration by iteration)
     float inv;      // 1/log2(1-p) <= 0; a value > 0 means flips disabled (p == 0)
     double p;
     short tgt[24];
@@ -997,6 +998,8 @@ struct SsdLoopArgs {
     u32 *sst;
     int iters;
     u32 nvalid;
+    u32 *flipbuf;  // per block: [warps][win][w32][32] words, or nullptr (no windowed path)
+    int win;
 };
 
 // inclusive warp prefix sum; shfl.up's predicate output says whether the source lane exists, so each step is two
@@ -1040,6 +1043,25 @@ __device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX
     if (ps.evp != 0xFFFFFFFFu) ps.evp -= W;
     ps.last_p1 -= W;
     __syncwarp();
+}
+
+// The same renewal process, with the events of one iteration recorded in a flip mask [w32][32] (word w of chain tl at
+// buf[w*32 + tl]) instead of being applied: the windowed loop below draws the masks of several iterations ahead.
+template <bool FULL>
+__device__ __forceinline__ void ssd_perturb_buf(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, u32 *buf, u32 W, float inv, u32 nvalid) {
+    for (;;) {
+        if (ps.evp < W) {
+            const u32 tl = ps.evp & 31u;
+            if (FULL || tl < nvalid) atomicXor(buf + ((ps.evp >> 10) << 5) + tl, 1u << ((ps.evp >> 5) & 31u));
+            ps.evp = 0xFFFFFFFFu;
+        }
+        if (ps.last_p1 > W) break;
+        const u32 pre = warp_scan_add(1u + geom_gap(dp.next(), inv));
+        ps.evp = ps.last_p1 - 1u + pre;
+        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+    }
+    if (ps.evp != 0xFFFFFFFFu) ps.evp -= W;
+    ps.last_p1 -= W;
 }
 
 struct SsdCount {
@@ -1158,6 +1180,49 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
         d.blk = ublk;  // the stream object takes over where the static part stopped (block boundary)
         d.have = 0;
     }
+    if constexpr (MODE == PBN_DRAW_PHILOX && HAS_ENV) {
+        // WINDOWED path (step-until-attractor inside every iteration): the number of updates per iteration is heavy-tailed,
+        // and iteration by iteration a warp would wait for its slowest chain every time.  The perturbation stream does not
+        // depend on the states, so the flip masks of the next `win` iterations are drawn first (warp-cooperatively, as
+        // always); then every chain runs through those iterations at its own pace in a flat loop whose trip is "start an
+        // iteration" or "one attractor test + at most one update", and the warp only waits once per window.
+        if (a.flipbuf != nullptr && !a.ev.force) {
+            const int w32 = nv.w32;
+            u32 *fb = a.flipbuf + (size_t)(threadIdx.x >> 5) * a.win * w32 * 32;
+            while (t < a.iters) {
+                const int kk = a.iters - t < a.win ? a.iters - t : a.win;
+                for (int k = 0; k < kk; k++) {
+                    for (int w = 0; w < w32; w++) fb[(k * w32 + w) * 32 + lane] = 0u;
+                    __syncwarp();
+                    if (flips) ssd_perturb_buf<FULL>(ps, dp, fb + k * w32 * 32, W, inv, a.nvalid);
+                }
+                __syncwarp();
+                int k = 0, in = 0;
+                bool start = true;
+                for (;;) {
+                    const bool live = active && k < kk;
+                    if (!__any_sync(0xFFFFFFFFu, live)) break;
+                    if (live) {
+                        if (start) {
+                            ssd_count(cnt, a, st);
+                            for (int w = 0; w < w32; w++) st.set_word(w, st.word(w) ^ fb[(k * w32 + w) * 32 + lane]);
+                            micro_step<NET, MODE, TQ>(nv, a.blob, st, d);  // env.step(0): pbn_target.py:269-271
+                            in = 1;
+                            start = false;
+                        } else if (in >= a.ev.max_inner || is_attracting(a.ev, a.att_off, a.cubes, st, w32)) {
+                            k++;
+                            start = true;
+                        } else {
+                            micro_step<NET, MODE, TQ>(nv, a.blob, st, d);
+                            in++;
+                        }
+                    }
+                }
+                __syncwarp();
+                t += kk;
+            }
+        }
+    }
     for (; t < a.iters; t++) {
         if (active) ssd_count(cnt, a, st);
         if constexpr (MODE == PBN_DRAW_REPLAY) {
@@ -1215,6 +1280,8 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
     const int w32 = nv.w32;
     const u32 n = (u32)nv.n;
     Col st{sst + threadIdx.x};
+    const int win = sp.win;
+    u32 *flipbuf = (HAS_ENV && win > 0) ? sst + w32 * PBN_BLOCK : nullptr;
     const bool active = e < chains;
     if (active) load_state(st, state, chains, e, w32);
     __syncthreads();
@@ -1226,7 +1293,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
         d.init(dv, e, env0 + e);
         dp.init_perturb(dv, e, env0 + e);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
-        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid};
+        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid, flipbuf, win};
         if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d, dp);   // every lane owns a chain: no predication
         else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d, dp);
         if (active) {
@@ -1563,7 +1630,10 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     EnvView ev;
     memset(&ev, 0, sizeof ev);
     if (env) ev = env->v;
-    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4;
+    // windowed step-until-attractor path: flip masks of `win` iterations per warp, 2 KB per warp (networks up to 256 nodes)
+    sp.win = (env && draws->mode == PBN_DRAW_PHILOX && !ev.force && nv.w32 <= 8) ? (16 / nv.w32 > 2 ? 16 / nv.w32 : 2) : 0;
+    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4 +
+                        (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4;
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                                                  \
     if (env) {                                                                                            \
