@@ -762,7 +762,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 template <int TQ, int G>  // G = 32: the whole warp on one env (group size known at compile time); G = 0: run-time group size g
 __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
                                         const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
-                                        bool active, int g_rt) {
+                                        bool active, int g_rt, u32 pos_base = 0u) {
+    // pos_base = updates the env's stream had served before this env.step began (0 for the env kernels, the running count
+    // of the launch for the SSD kernel): update number `in` of the step takes words 2*(pos_base + in), +1
     const int g = G > 0 ? G : g_rt;
     const u32 lane = threadIdx.x & 31u;
     const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
@@ -786,7 +788,7 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
         if (running && (in >= ev.max_inner || (votes & gmask) != 0u)) running = false;
         if (!__any_sync(0xFFFFFFFFu, running)) break;
         if (running && u == batch) {  // g blocks of the update stream from word 2*in on (uniform inside a group)
-            const u32 a = 2u * (u32)in;
+            const u32 a = 2u * (pos_base + (u32)in);
             off = a & 3u;
             philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
             u = 0;
@@ -1000,6 +1002,7 @@ struct SsdLoopArgs {
     u32 nvalid;
     u32 *flipbuf;  // per block: [warps][win][w32][32] words, or nullptr (no windowed path)
     int win;
+    long long chain_id;  // global id of this thread's chain (Philox counter words 2, 3)
 };
 
 // inclusive warp prefix sum; shfl.up's predicate output says whether the source lane exists, so each step is two
@@ -1189,6 +1192,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
         if (a.flipbuf != nullptr && !a.ev.force) {
             const int w32 = nv.w32;
             u32 *fb = a.flipbuf + (size_t)(threadIdx.x >> 5) * a.win * w32 * 32;
+            u32 pos = 0;  // updates this chain's stream has served so far in this launch
             while (t < a.iters) {
                 const int kk = a.iters - t < a.win ? a.iters - t : a.win;
                 for (int k = 0; k < kk; k++) {
@@ -1208,6 +1212,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                             for (int w = 0; w < w32; w++) st.set_word(w, st.word(w) ^ fb[(k * w32 + w) * 32 + lane]);
                             micro_step<NET, MODE, TQ>(nv, a.blob, st, d);  // env.step(0): pbn_target.py:269-271
                             in = 1;
+                            pos++;
                             start = false;
                         } else if (in >= a.ev.max_inner || is_attracting(a.ev, a.att_off, a.cubes, st, w32)) {
                             k++;
@@ -1215,6 +1220,34 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                         } else {
                             micro_step<NET, MODE, TQ>(nv, a.blob, st, d);
                             in++;
+                            pos++;
+                        }
+                    }
+                    if constexpr (NET == PBN_NET_PRED) {
+                        // straggler mode (see coop_run): the last chains of the warp inside their attractor loops are finished
+                        // by groups of lanes, all groups at once
+                        const unsigned hv = __ballot_sync(0xFFFFFFFFu, live && !start && k < kk);
+                        if (hv != 0u && __popc(__ballot_sync(0xFFFFFFFFu, active && k < kk)) <= PBN_COOP_MAX) {
+                            const int nl = __popc(hv);
+                            int kg = 1;
+                            while (kg < nl) kg <<= 1;
+                            const int g = 32 / kg, grp = (int)lane / g;
+                            const bool on = grp < nl;
+                            const int owner = on ? (int)__fns(hv, 0u, grp + 1) : 0;
+                            const long long idL = __shfl_sync(0xFFFFFFFFu, a.chain_id, owner);
+                            const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
+                            const u32 baseL = __shfl_sync(0xFFFFFFFFu, pos - (u32)in, owner);
+                            u32 *colL = a.sst + (threadIdx.x & ~31u) + (u32)owner;
+                            const int fin = coop_run<TQ, 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL);
+                            for (int r = 0; r < nl; r++) {
+                                const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
+                                if ((int)lane == (int)__fns(hv, 0u, r + 1) && v != in) {
+                                    pos += (u32)(v - in);
+                                    in = v;
+                                    d.seek(a.dv, 0, a.chain_id, 2u * pos, 0u);  // later iterations go on drawing from this stream
+                                }
+                            }
+                            __syncwarp();
                         }
                     }
                 }
@@ -1293,7 +1326,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
         d.init(dv, e, env0 + e);
         dp.init_perturb(dv, e, env0 + e);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
-        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid, flipbuf, win};
+        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid, flipbuf, win, env0 + e};
         if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d, dp);   // every lane owns a chain: no predication
         else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d, dp);
         if (active) {
