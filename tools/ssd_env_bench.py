@@ -1,7 +1,14 @@
-import sys, time
-sys.path.insert(0, 'gym-pbn-stac_b200')
-import numpy as np, torch
-from gym_PBN.b200 import abi, compiler, engine, attractors
+"""SSD estimation with the step-until-attractor loop inside every iteration (env given): Bittner-28 with its exact
+attractors, cap 4 096, random start states.  python tools/ssd_env_bench.py"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / 'gym-pbn-stac_b200'))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from gym_PBN.b200 import abi, attractors, compiler, engine  # noqa: E402
+
 net = engine.Network(compiler.load_bittner("28_15_median"))
 atts = attractors.exact_attractor_cubes(net)
 env = engine.EnvImage(net, abi.ENV_TARGET, attractors=atts, horizon=100, max_inner=4096)
