@@ -778,16 +778,17 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
     u32 off = 0;
     bool running = active;
     for (;;) {
+        // every lane runs the same instruction stream whether or not its group is still running (a finished or unused group
+        // recomputes on its column and commits nothing): no divergent regions inside the loop
         bool hit = false;
-        if (running)
-            for (int c0 = 0; c0 < n_cubes; c0 += g) {
-                const int c = c0 + (int)sub;
-                hit |= c < n_cubes && cube_match(cubes, c, st, w32);
-            }
+        for (int c0 = 0; c0 < n_cubes; c0 += g) {
+            const int c = c0 + (int)sub;
+            hit |= c < n_cubes && cube_match(cubes, c, st, w32);
+        }
         const unsigned votes = __ballot_sync(0xFFFFFFFFu, hit);
-        if (running && (in >= ev.max_inner || (votes & gmask) != 0u)) running = false;
+        running = running && in < ev.max_inner && (votes & gmask) == 0u;
         if (!__any_sync(0xFFFFFFFFu, running)) break;
-        if (running && u == batch) {  // g blocks of the update stream from word 2*in on (uniform inside a group)
+        if (u == batch) {  // g blocks of the update stream from word 2*(pos_base + in) on (uniform inside a group)
             const u32 a = 2u * (pos_base + (u32)in);
             off = a & 3u;
             philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
@@ -799,9 +800,9 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
         const u32 src = gbase + ((w >> 2) & (u32)(g - 1));
         const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, src);
         const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, src);
+        const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
+        const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
         if (running) {
-            const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
-            const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
             st.put(i, v);
             in++;
             u++;
