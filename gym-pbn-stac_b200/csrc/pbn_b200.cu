@@ -811,6 +811,79 @@ __device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, co
     return in;
 }
 
+// The same for networks of at most 32 nodes (one state word: the 28-gene Bittner set of BASELINE config 2): the state lives
+// in a REGISTER of every lane of the group for the whole run, so the attractor test, the four input gathers and the write-back
+// involve no shared-memory round trip; what is left on the dependent chain of an update is one vote, the threshold and record
+// loads.  One ballot per trip serves both the group's own test and the exit test (finished, capped and unused groups keep
+// voting "done").
+template <int TQ, int G>
+__device__ __forceinline__ int coop_run_w1(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
+                                           const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
+                                           bool active, int g_rt, u32 pos_base = 0u) {
+    const int g = G > 0 ? G : g_rt;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
+    const u32 gmask = (g == 32 ? 0xFFFFFFFFu : ((1u << g) - 1u)) << gbase;
+    // bit r*g set for every group r: after OR-folding the ballot inside the groups these bits say "group r is done"
+    const u32 heads = g == 32 ? 1u : (g == 16 ? 0x00010001u : (g == 8 ? 0x01010101u : (g == 4 ? 0x11111111u : 0x55555555u)));
+    const int n_cubes = att_off[ev.n_att];
+    const uint4 *thr_rows = reinterpret_cast<const uint4 *>(blob + nv.off_thr);
+    const uint2 *recs = reinterpret_cast<const uint2 *>(blob + nv.off_rec);
+    u32 st = *col_ptr;
+    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    int u = 0, batch = 0;
+    u32 off = 0;
+    bool running = active;
+    for (;;) {
+        bool hit = false;
+        for (int c0 = 0; c0 < n_cubes; c0 += g) {
+            const int c = c0 + (int)sub;
+            if (c < n_cubes) hit |= (st & cubes[2 * c]) == cubes[2 * c + 1];
+        }
+        u32 b = __ballot_sync(0xFFFFFFFFu, hit || !running || in >= ev.max_inner);
+        running = running && in < ev.max_inner && (b & gmask) == 0u;
+        for (int sft = 1; sft < g; sft <<= 1) b |= b >> sft;  // OR inside each group lands on the group's lowest bit
+        if ((b & heads) == heads) break;                       // every group done
+        if (u == batch) {  // g blocks of the update stream from word 2*(pos_base + in) on (uniform inside a group)
+            const u32 a = 2u * (pos_base + (u32)in);
+            off = a & 3u;
+            philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
+            u = 0;
+            batch = (int)((4u * (u32)g - off) >> 1);
+        }
+        const u32 w = off + 2u * (u32)u;
+        const bool hi_pair = (w & 2u) != 0u;
+        const u32 src = gbase + ((w >> 2) & (u32)(g - 1));
+        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, src);
+        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, src);
+        const u32 i = (u32)nv.first + __umulhi(wa, (u32)(nv.n - nv.first));
+        const u32 r = wb >> 1;
+        const uint4 *thr = thr_rows + i * nv.tsq_stride;
+        u32 j;
+        if (TQ == 1) {
+            const uint4 t = thr[0];
+            j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        } else {
+            const uint4 m = thr[0];
+            u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
+            q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
+            const uint4 t = thr[1 + q];
+            j = 4u * q + (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        }
+        const uint2 rec = recs[i * nv.fmax + j];
+        const u32 idx = (((st >> (rec.x & 31u)) & 1u) << 3) | (((st >> ((rec.x >> 8) & 31u)) & 1u) << 2) |
+                        (((st >> ((rec.x >> 16) & 31u)) & 1u) << 1) | ((st >> ((rec.x >> 24) & 31u)) & 1u);
+        const u32 v = (rec.y >> idx) & 1u;
+        if (running) {
+            st = (st & ~(1u << i)) | (v << i);
+            in++;
+            u++;
+        }
+    }
+    if (active) *col_ptr = st;  // every lane of the group holds the same word
+    return in;
+}
+
 template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
@@ -927,7 +1000,8 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
                         const long long eL = __shfl_sync(0xFFFFFFFFu, e, L);
                         const int inL = __shfl_sync(0xFFFFFFFFu, in, L);
                         u32 *colL = sst + (threadIdx.x & ~31u) + (u32)L;
-                        take_back(L, coop_run<TQ, 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32));
+                        take_back(L, (TQ > 0 && w32 == 1) ? coop_run_w1<(TQ > 0 ? TQ : 1), 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32)
+                                                      : coop_run<TQ, 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32));
                     }
                 } else {
                     const int nl = __popc(hv);
@@ -940,7 +1014,8 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
                     const long long eL = __shfl_sync(0xFFFFFFFFu, e, owner);
                     const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
                     u32 *colL = sst + (threadIdx.x & ~31u) + (u32)owner;
-                    const int fin = coop_run<TQ, 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g);
+                    const int fin = (TQ > 0 && w32 == 1) ? coop_run_w1<(TQ > 0 ? TQ : 1), 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g)
+                                                         : coop_run<TQ, 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g);
                     for (int r = 0; r < nl; r++)            // hand each group's count back to the lane that owns the env
                         take_back((int)__fns(hv, 0u, r + 1), __shfl_sync(0xFFFFFFFFu, fin, r * g));
                 }
@@ -1239,7 +1314,9 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                             const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
                             const u32 baseL = __shfl_sync(0xFFFFFFFFu, pos - (u32)in, owner);
                             u32 *colL = a.sst + (threadIdx.x & ~31u) + (u32)owner;
-                            const int fin = coop_run<TQ, 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL);
+                            const int fin = (TQ > 0 && w32 == 1)
+                                                ? coop_run_w1<(TQ > 0 ? TQ : 1), 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL)
+                                                : coop_run<TQ, 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL);
                             for (int r = 0; r < nl; r++) {
                                 const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
                                 if ((int)lane == (int)__fns(hv, 0u, r + 1) && v != in) {
