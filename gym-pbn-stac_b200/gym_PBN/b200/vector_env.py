@@ -24,9 +24,7 @@ def _family(env):
     from gym_PBN.envs.pbn_target_multi import PBNTargetMultiEnv
 
     if "SelfTriggering" in type(env).__name__:
-        raise TypeError("self-triggering envs return float64 discounted rewards; step them in batches with engine.Simulator.env_step "
-                        "(env kinds ENV_PBN_ST / ENV_PBCN_ST, results in sim.reward_f64 / sim.inner) — the fused vector step keeps "
-                        "integer episode returns")
+        return "st"
     if isinstance(env, PBNTargetMultiEnv):
         return "multi"
     if isinstance(env, PBNTargetEnv):
@@ -59,7 +57,13 @@ class PBNVectorEnv:
         self.single_action_space = env.action_space
         self.max_inner_steps = int(max_inner_steps if max_inner_steps is not None else getattr(env, "max_inner_steps", 1))
         self.action_slots = action_slots
-        if self.family == "pbn":
+        if self.family == "st":
+            # self-triggering macro steps (envs/self_triggering.py): one launch of the macro-step kernel, float64 discounted
+            # rewards; bookkeeping and the masked reset follow as separate small launches (no fused epilogue for float returns)
+            self.image = env._st_image()
+            self.action_width = 2 if self.image.kind == abi.ENV_PBN_ST else 1 + env.PBN.M  # (primitive, prob) | (prob, control..)
+            self.horizon = 0
+        elif self.family == "pbn":
             kind = next(_KIND_OF[c.__name__] for c in type(env).__mro__ if c.__name__ in _KIND_OF)  # most derived class first
             self.image = engine.EnvImage(
                 self.network, kind, attractors=[sorted(a) for a in env.all_attractors], targets=sorted(env.target_nodes),
@@ -75,7 +79,9 @@ class PBNVectorEnv:
             self.action_width = 1 if self.family == "target" else action_slots
             self.horizon = env.horizon
         self.stats = pdist.EpisodeStats(self.device)
-        self.ep_return = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64 if self.family == "st" else torch.int64,
+                                     device=self.device)
+        self.return_sum_f64 = torch.zeros((), dtype=torch.float64, device=self.device)  # "st": stats.v[1] stays 0
         self.ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self.final_obs = torch.zeros_like(self.sim.state)
         self._needs_reset = True
@@ -113,12 +119,41 @@ class PBNVectorEnv:
         if actions.numel() != self.num_envs * self.action_width:
             raise ValueError(f"actions must have shape [{self.num_envs}, {self.action_width}]")
         sim = self.sim
+        if self.family == "st":
+            return self._step_self_triggering(actions)
         # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)
         sim.vec_step(self.image, actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
                      autoreset=self.autoreset)
         info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state, "final_obs_packed": self.final_obs}
         # after the launch obs_state holds the step's observation, or the NEW state for envs that were auto-reset
         return self._obs(sim.obs_state), sim.reward, sim.terminated, sim.truncated, info
+
+    def _step_self_triggering(self, actions):
+        """Macro step of every env (actions int32 [B][2] = (primitive, prob) for the PBN variant, [B][1+M] = (prob, control
+        bits) for the PBCN variant); rewards are float64 [B], info["interval"] the primitive steps each env took.  Same draw
+        consumption as Simulator.env_step followed by a masked Simulator.env_reset (one epoch each)."""
+        sim = self.sim
+        sim.env_step(self.image, actions)
+        reward, term, trunc = sim.reward_f64, sim.terminated, sim.truncated
+        done = term | trunc
+        self.ep_return += reward
+        self.ep_len += 1
+        v = self.stats.v
+        n_done = done.sum()
+        v[0] += n_done
+        v[2] += (self.ep_len * done).sum()
+        v[3] += term.sum()
+        v[5] += self.num_envs
+        self.return_sum_f64 += (self.ep_return * done).sum()
+        self.final_obs.copy_(sim.state)
+        self.ep_return.masked_fill_(done, 0.0)
+        self.ep_len.masked_fill_(done, 0)
+        if self.autoreset:
+            sim.env_reset(self.image, mask=done)
+        else:
+            sim.epoch += 1  # keep the epoch schedule independent of the flag
+        info = {"interval": sim.inner, "inner_steps": sim.inner, "packed_obs": sim.state, "final_obs_packed": self.final_obs}
+        return self._obs(sim.state), reward, term, trunc, info
 
     def step_host(self, actions_host):
         """Host in / host out convenience (pinned staging): NumPy actions -> NumPy (obs, reward, terminated, truncated)."""

@@ -732,3 +732,54 @@ def test_env_classes_replay_reference_traces():
                 return env.step(acts if as_list else torch.tensor(acts))
 
             _class_level_replay(env, tr, K, step, on_reset)
+
+
+@pytest.mark.parametrize("tag", ["pbn", "pbcn"])
+def test_vector_env_self_triggering_matches_oracle(tag):
+    """PBNVectorEnv over the self-triggering envs: macro step + masked auto-reset against the oracle (float64 rewards,
+    intervals, observations, episode statistics), epoch for epoch."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+    from gym_PBN.utils.converters import logic_funcs_to_PBN_data
+
+    T = 5 if tag == "pbn" else 7
+    env_id = "gym-PBN/PBN-self-triggering-v0" if tag == "pbn" else "gym-PBN/PBCN-self-triggering-v0"
+    env = gym_PBN.make(env_id, logic_func_data=EX5, goal_config=dict(GOAL), gamma=0.9, T=T).unwrapped
+    B, seed = 1500, 9
+    vec = PBNVectorEnv(env, B, seed=seed)
+    assert vec.family == "st" and vec.action_width == 2
+    okind = orc.ENV_PBN_ST if tag == "pbn" else orc.ENV_PBCN_ST
+    atts = [sorted(a) for a in env.all_attractors]
+    oenv = orc.Env(okind, 5, attractors=atts, targets=env._target_states(), n_control=getattr(env.PBN, "M", 0),
+                   successful_reward=env.successful_reward, wrong_attractor_cost=env.wrong_attractor_cost, gamma=0.9,
+                   max_interval=T)
+    onet = orc.net_from_pbn_data(logic_funcs_to_PBN_data(*EX5))
+    ost, ons, ota = np.zeros((B, 5), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    obs, _ = vec.reset()
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    assert np.array_equal(obs.cpu().numpy(), ost)
+    rng = np.random.default_rng(2)
+    ep_ret, ep_len = np.zeros(B), np.zeros(B, np.int64)
+    episodes = successes = 0
+    ret_sum = 0.0
+    for t in range(6):
+        act = (np.stack([rng.integers(0, 6, B), rng.integers(1, 11, B)], 1) if tag == "pbn"
+               else np.stack([rng.integers(1, 11, B), rng.integers(0, 2, B)], 1)).astype(np.int32)
+        obs, r, te, tr, info = vec.step(torch.from_numpy(act))
+        _o, rf, term, inner = orc.env_step_f64(onet, oenv, ost, act, orc.Draws(seed=seed, epoch=1 + 2 * t))
+        assert np.array_equal(vec.final_obs.cpu().numpy()[0], (ost.astype(np.int32) << np.arange(5)).sum(1)), t  # before the reset
+        done = term.astype(bool)
+        orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=2 + 2 * t), mask=done)
+        assert np.array_equal(obs.cpu().numpy(), ost), t
+        assert np.array_equal(r.cpu().numpy(), rf) and r.dtype == torch.float64, t
+        assert np.array_equal(te.cpu().numpy(), done) and not tr.any(), t
+        assert np.array_equal(info["interval"].cpu().numpy(), inner), t
+        ep_ret += rf
+        ep_len += 1
+        episodes += int(done.sum()); successes += int(done.sum())
+        ret_sum += float((ep_ret * done).sum())
+        ep_ret[done] = 0; ep_len[done] = 0
+        assert np.array_equal(vec.ep_return.cpu().numpy(), ep_ret) and np.array_equal(vec.ep_len.cpu().numpy(), ep_len), t
+    s = vec.stats.reduced()
+    assert s["episodes"] == episodes and s["successes"] == successes and s["env_steps"] == 6 * B and episodes > 0
+    assert abs(float(vec.return_sum_f64) - ret_sum) < 1e-9 * max(1.0, abs(ret_sum))
