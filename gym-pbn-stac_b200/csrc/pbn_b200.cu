@@ -276,23 +276,32 @@ struct SsdFast {
     float inv;
 };
 
+// 8 * #{k : t[k] <= r} for an ascending quad of thresholds (cumulative COD rows are ascending, so the predicates are
+// monotone and a select chain replaces the sum): 4 compares + 4 selects
+__device__ __forceinline__ u32 count_le_x8(const uint4 t, u32 r) {
+    u32 j8;
+    asm("{ .reg .pred p0, p1, p2, p3;\n\t"
+        "setp.le.u32 p0, %1, %5; setp.le.u32 p1, %2, %5; setp.le.u32 p2, %3, %5; setp.le.u32 p3, %4, %5;\n\t"
+        "selp.u32 %0, 8, 0, p0; selp.u32 %0, 16, %0, p1; selp.u32 %0, 24, %0, p2; selp.u32 %0, 32, %0, p3; }"
+        : "=r"(j8) : "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w), "r"(r));
+    return j8;
+}
+
 // one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312)
 template <int TQ>
 __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
     const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
     const u32 r = wb >> 1;
-    u32 j;
+    u32 j8;  // 8 * (index of the selected predictor)
     if constexpr (TQ == 1) {
-        const uint4 t = ldc_v4(f.thr + i * f.thr_stride);
-        j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        j8 = count_le_x8(ldc_v4(f.thr + i * f.thr_stride), r);
     } else {  // leading quad = last threshold of each quad (at most four quads when TQ is known)
         const uint4 m = ldc_v4(f.thr + i * f.thr_stride);
         u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
         q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
-        const uint4 t = ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u);
-        j = 4u * q + (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
+        j8 = 32u * q + count_le_x8(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
     }
-    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j * 8u);
+    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j8);
     const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
     const u32 w0 = lds_u32(f.col + ((p0 & 0xE0u) << 5));
     const u32 w1 = lds_u32(f.col + ((p1 & 0xE0u) << 5));
@@ -302,11 +311,10 @@ __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb
     idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
     idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
     idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
-    const u32 v = (rec.y >> idx) & 1u;
     const u32 wa_addr = f.col + ((i & ~31u) << 5);
     const u32 m = 1u << (i & 31u);
     const u32 old = lds_u32(wa_addr);
-    sts_u32(wa_addr, (old & ~m) | (v ? m : 0u));
+    sts_u32(wa_addr, (old & ~m) | (((rec.y >> idx) << (i & 31u)) & m));  // bit i <- LUT bit idx (one select)
 }
 
 static DrawView make_draws(const PbnDraws *d) {
@@ -1157,19 +1165,20 @@ __device__ __forceinline__ void ssd_count(SsdCount &c, const SsdLoopArgs &a, con
     c.run++;
 }
 
+// "No pending event" is any value >= W here: 0xFFFFFFFF is only ever lowered by W per iteration until the next round
+// overwrites it, and a round comes at the latest after 32 capped gaps (< 2^31 positions), so it never reaches the window.
 __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, const DrawView &dv) {
     for (;;) {
-        if (ps.evp < f.W) {
-            // word (node>>5) of column (evp&31): byte offset = (evp&31)*4 + (node>>5)*1024, node = evp>>5
-            red_xor_u32(f.warp_cols + (((ps.evp << 2) & 0x7Cu) | (ps.evp & 0xFFFFFC00u)), 1u << ((ps.evp >> 5) & 31u));
-            ps.evp = 0xFFFFFFFFu;
-        }
-        if (ps.last_p1 > f.W) break;
+        // word (node>>5) of column (evp&31): byte offset = (evp&31)*4 + (node>>5)*1024, node = evp>>5; predicated, no branch
+        asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p red.shared.xor.b32 [%2], %3; }"
+                     :: "r"(ps.evp), "r"(f.W), "r"(f.warp_cols + (((ps.evp << 2) & 0x7Cu) | (ps.evp & 0xFFFFFC00u))),
+                        "r"(1u << ((ps.evp >> 5) & 31u)) : "memory");
+        if (ps.last_p1 > f.W) break;  // otherwise every pending event lay inside this window and has just been applied
         const u32 pre = warp_scan_add(1u + geom_gap(dp.next_rk(dv), f.inv));
         ps.evp = ps.last_p1 - 1u + pre;
         ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
     }
-    if (ps.evp != 0xFFFFFFFFu) ps.evp -= f.W;
+    ps.evp = ps.evp < f.W ? 0xFFFFFFFFu : ps.evp - f.W;
     ps.last_p1 -= f.W;
     __syncwarp();
 }
@@ -1199,11 +1208,11 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     u32 cur = (u32)cnt.cur, run = cnt.run;
     auto count = [&]() {
         const u32 b = __brev((lds_u32(f.col + f.b_off) >> f.b_sh) << f.b_up);
-        if (b != cur) {
-            red_add_u32(f.shist + cur * 4u, run);
-            cur = b; run = 0;
-        }
-        run++;
+        u32 r0;  // run-length aggregation, predicated: flush the run when the bucket changes
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, %2; @p red.shared.add.u32 [%3], %4; selp.u32 %0, 0, %4, p; }"
+                     : "=r"(r0) : "r"(b), "r"(cur), "r"(f.shist + cur * 4u), "r"(run) : "memory");
+        cur = b;
+        run = r0 + 1u;
     };
     for (; t + 1 < a.iters; t += 2) {
         u32 x0, x1, x2, x3;
