@@ -29,6 +29,9 @@ int pbn_fail_(int code, const std::string &msg) { return fail(code, msg); }  // 
 extern "C" const char *pbn_last_error(void) { return g_err.c_str(); }
 extern "C" const char *pbn_version(void) { return "pbn_b200 0.1 (sm_100a)"; }
 
+#ifndef PBN_REC16_MAX
+#define PBN_REC16_MAX (32 * 1024)  // predictor networks get the 16-byte fast-path records when they fit this many bytes
+#endif
 #ifndef PBN_TT_THR_SMEM_MAX
 #define PBN_TT_THR_SMEM_MAX (16 * 1024)
 #endif
@@ -114,6 +117,24 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
                 rec[i * fmax + k] = make_uint2(packed, d->pr_lut[q]);
             }
         }
+        if ((size_t)n * fmax * 16 <= PBN_REC16_MAX) {
+            // 16-byte records of the fast asynchronous paths (ssd_fast_update), appended to the image and staged only by
+            // them: x = f0 | f1 << 16, y = f2 | f3 << 16 with f_j = (word of input j) << 10 | rotate amount that brings the
+            // input's bit to position 3 - j; z = the 16-bit LUT in both halves (the index may carry garbage in bit 4); w = 0
+            v.off_rec16 = (int)((blob.size() + 15) & ~(size_t)15);
+            blob.resize((size_t)v.off_rec16 + (size_t)n * fmax * 16);
+            uint4 *r16 = reinterpret_cast<uint4 *>(blob.data() + v.off_rec16);
+            const uint2 *r8 = reinterpret_cast<const uint2 *>(blob.data() + v.off_rec);
+            for (int q = 0; q < n * fmax; q++) {
+                u32 fld[4];
+                for (int j = 0; j < 4; j++) {
+                    const u32 pj = (r8[q].x >> (8 * j)) & 0xFFu;
+                    fld[j] = ((pj >> 5) << 10) | (((pj & 31u) - (3u - (u32)j)) & 31u);
+                }
+                const u32 lut = r8[q].y & 0xFFFFu;
+                r16[q] = make_uint4(fld[0] | (fld[1] << 16), fld[2] | (fld[3] << 16), lut | (lut << 16), 0u);
+            }
+        }
         if (fmax <= 5) {  // mask table of the bit-sliced synchronous kernel
             const int lrow = fmax * 16 + 4;  // +16 B per node: consecutive nodes (lanes) start in different bank groups
             std::vector<u32> lm((size_t)n * lrow, 0u);
@@ -160,7 +181,8 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         return fail(PBN_ERR_ARG, "unknown network kind");
     }
     blob.resize((blob.size() + 15) & ~(size_t)15);
-    v.blob_bytes = (int)blob.size();
+    v.blob_bytes = v.blob_fast_bytes = (int)blob.size();
+    if (v.off_rec16) v.blob_bytes = v.off_rec16;  // everything but the fast paths stages the image without the 16-byte records
     rc |= upload(net->owned, blob.data(), blob.size(), &v.blob);
     if (rc) { pbn_net_destroy(net); return PBN_ERR_CUDA; }
     v.thr_dev = nullptr;
@@ -169,7 +191,7 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         // global memory and is read through the L1 (one load per update); only node records and input lists are staged.
         // With the 32-word state columns of a 1024-node network the image would otherwise limit an SM to two blocks.
         v.thr_dev = reinterpret_cast<const u32 *>(v.blob + v.off_thr);
-        v.blob_bytes = v.off_thr;
+        v.blob_bytes = v.blob_fast_bytes = v.off_thr;
     }
     if (v.blob_bytes > 160 * 1024) { pbn_net_destroy(net); return fail(PBN_ERR_UNSUPPORTED, "network image exceeds shared memory"); }
     *out = net;
@@ -264,11 +286,26 @@ __device__ __forceinline__ uint4 ldc_v4(u32 a) {  // read-only image data: free 
 __device__ __forceinline__ uint2 ldc_v2(u32 a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ u32 keep(u32 x) { asm volatile("" : "+r"(x)); return x; }  // pins a loop invariant in a register
 
+// State columns of networks up to 256 nodes start on a power-of-two boundary >= w32 KB of the shared window, so that
+// "column address + word offset" is an OR and folds into the LOP3 that masks the offset (fast paths below).
+__host__ __device__ inline unsigned col_align_bytes(int w32) {
+    if (w32 > 8) return 0u;
+    unsigned a = 1024u;
+    while (a < (unsigned)w32 * 1024u) a <<= 1;
+    return a;
+}
+__device__ __forceinline__ u32 *align_cols(u32 *p, int w32) {
+    const u32 al = col_align_bytes(w32);
+    if (!al) return p;
+    const u32 a = smem_addr(p);
+    return reinterpret_cast<u32 *>(reinterpret_cast<char *>(p) + ((al - (a & (al - 1u))) & (al - 1u)));
+}
+
 // Loop invariants of the predictor-network SSD loop, as registers.
 struct SsdFast {
     u32 col;        // shared address of this thread's state column (word w at col + w*1024)
     u32 warp_cols;  // shared address of lane 0's column of this warp
-    u32 thr, rec;   // shared addresses of the threshold rows / predictor records
+    u32 thr, rec;   // shared addresses of the threshold rows / 16-byte predictor records
     u32 thr_stride, rec_stride;  // bytes per node
     u32 shist;      // shared address of the block histogram
     u32 n, W;
@@ -276,13 +313,13 @@ struct SsdFast {
     float inv;
 };
 
-// 8 * #{k : t[k] <= r} for an ascending quad of thresholds (cumulative COD rows are ascending, so the predicates are
+// 16 * #{k : t[k] <= r} for an ascending quad of thresholds (cumulative COD rows are ascending, so the predicates are
 // monotone and a select chain replaces the sum): 4 compares + 4 selects
-__device__ __forceinline__ u32 count_le_x8(const uint4 t, u32 r) {
+__device__ __forceinline__ u32 count_le_x16(const uint4 t, u32 r) {
     u32 j8;
     asm("{ .reg .pred p0, p1, p2, p3;\n\t"
         "setp.le.u32 p0, %1, %5; setp.le.u32 p1, %2, %5; setp.le.u32 p2, %3, %5; setp.le.u32 p3, %4, %5;\n\t"
-        "selp.u32 %0, 8, 0, p0; selp.u32 %0, 16, %0, p1; selp.u32 %0, 24, %0, p2; selp.u32 %0, 32, %0, p3; }"
+        "selp.u32 %0, 16, 0, p0; selp.u32 %0, 32, %0, p1; selp.u32 %0, 48, %0, p2; selp.u32 %0, 64, %0, p3; }"
         : "=r"(j8) : "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w), "r"(r));
     return j8;
 }
@@ -292,29 +329,30 @@ template <int TQ>
 __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
     const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
     const u32 r = wb >> 1;
-    u32 j8;  // 8 * (index of the selected predictor)
+    u32 j16;  // 16 * (index of the selected predictor)
     if constexpr (TQ == 1) {
-        j8 = count_le_x8(ldc_v4(f.thr + i * f.thr_stride), r);
+        j16 = count_le_x16(ldc_v4(f.thr + i * f.thr_stride), r);
     } else {  // leading quad = last threshold of each quad (at most four quads when TQ is known)
         const uint4 m = ldc_v4(f.thr + i * f.thr_stride);
         u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
         q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
-        j8 = 32u * q + count_le_x8(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
+        j16 = 64u * q + count_le_x16(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
     }
-    const uint2 rec = ldc_v2(f.rec + i * f.rec_stride + j8);
-    const u32 p0 = rec.x, p1 = rec.x >> 8, p2 = rec.x >> 16, p3 = rec.x >> 24;
-    const u32 w0 = lds_u32(f.col + ((p0 & 0xE0u) << 5));
-    const u32 w1 = lds_u32(f.col + ((p1 & 0xE0u) << 5));
-    const u32 w2 = lds_u32(f.col + ((p2 & 0xE0u) << 5));
-    const u32 w3 = lds_u32(f.col + ((p3 & 0xE0u) << 5));
-    u32 idx = __funnelshift_r(w0, 0, p0) & 1u;
-    idx = idx * 2u + (__funnelshift_r(w1, 0, p1) & 1u);
-    idx = idx * 2u + (__funnelshift_r(w2, 0, p2) & 1u);
-    idx = idx * 2u + (__funnelshift_r(w3, 0, p3) & 1u);
-    const u32 wa_addr = f.col + ((i & ~31u) << 5);
-    const u32 m = 1u << (i & 31u);
+    const uint4 rec = ldc_v4(f.rec + i * f.rec_stride + j16);
+    const u32 f1 = rec.x >> 16, f3 = rec.y >> 16;
+    // columns are aligned (align_cols): column address | word offset; a rotate brings input j's bit to position 3 - j
+    const u32 w0 = lds_u32(f.col | (rec.x & 0x1C00u));
+    const u32 w1 = lds_u32(f.col | (f1 & 0x1C00u));
+    const u32 w2 = lds_u32(f.col | (rec.y & 0x1C00u));
+    const u32 w3 = lds_u32(f.col | (f3 & 0x1C00u));
+    u32 idx = (__funnelshift_r(w0, w0, rec.x) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
+    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, rec.y) & ~0xCu);
+    idx = (idx & 0xEu) | (__funnelshift_r(w3, w3, f3) & ~0xEu);  // bits 3..0: LUT index; above: garbage (shifts wrap, LUT doubled)
+    const u32 v = __funnelshift_r(rec.z, 0u, idx);
+    const u32 wa_addr = f.col | ((i & ~31u) << 5);
+    const u32 m = __funnelshift_l(0u, 1u, i);  // 1 << (i & 31)
     const u32 old = lds_u32(wa_addr);
-    sts_u32(wa_addr, (old & ~m) | (((rec.y >> idx) << (i & 31u)) & m));  // bit i <- LUT bit idx (one select)
+    sts_u32(wa_addr, (old & ~m) | (__funnelshift_l(0u, v, i) & m));  // bit i <- LUT bit idx
 }
 
 static DrawView make_draws(const PbnDraws *d) {
@@ -336,8 +374,9 @@ template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, u32 *state, long long B, long long env0,
                                                        long long steps, int sync) {
     unsigned char *blob = smem_raw;
-    u32 *sst = reinterpret_cast<u32 *>(smem_raw + nv.blob_bytes);
-    stage(blob, nv.blob, nv.blob_bytes);
+    const int bb = sync ? nv.blob_bytes : nv.blob_fast_bytes;  // asynchronous rollouts also stage the 16-byte records
+    u32 *sst = align_cols(reinterpret_cast<u32 *>(smem_raw + bb), nv.w32);
+    stage(blob, nv.blob, bb);
     const long long e = (long long)blockIdx.x * PBN_BLOCK + threadIdx.x;
     Col st{sst + threadIdx.x};
     Col tmp{sst + nv.w32 * PBN_BLOCK + threadIdx.x};
@@ -363,12 +402,13 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
             // an update takes exactly two words of the env's stream: one Philox block per two updates, no buffer bookkeeping
             u32 ublk = 0;
             if constexpr (NET == PBN_NET_PRED && TQ > 0) {
+              if (nv.off_rec16) {
                 SsdFast f;
                 f.col = keep(smem_addr(st.s));
                 f.thr = keep(smem_addr(blob + nv.off_thr));
-                f.rec = keep(smem_addr(blob + nv.off_rec));
+                f.rec = keep(smem_addr(blob + nv.off_rec16));
                 f.thr_stride = keep((u32)nv.tsq_stride * 16u);
-                f.rec_stride = keep((u32)nv.fmax * 8u);
+                f.rec_stride = keep((u32)nv.fmax * 16u);
                 f.n = keep((u32)nv.n);
                 for (; t + 1 < steps; t += 2) {
                     u32 x0, x1, x2, x3;
@@ -376,7 +416,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
                     ssd_fast_update<TQ>(f, x0, x1);
                     ssd_fast_update<TQ>(f, x2, x3);
                 }
-            } else {
+              }
+            }
+            {
                 for (; t + 1 < steps; t += 2) {
                     u32 x0, x1, x2, x3;
                     philox4x32_10_rk(ublk++, d.c1, d.c2, d.c3, dv, x0, x1, x2, x3);
@@ -1171,7 +1213,7 @@ __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &p
     for (;;) {
         // word (node>>5) of column (evp&31): byte offset = (evp&31)*4 + (node>>5)*1024, node = evp>>5; predicated, no branch
         asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p red.shared.xor.b32 [%2], %3; }"
-                     :: "r"(ps.evp), "r"(f.W), "r"(f.warp_cols + (((ps.evp << 2) & 0x7Cu) | (ps.evp & 0xFFFFFC00u))),
+                     :: "r"(ps.evp), "r"(f.W), "r"((f.warp_cols | ((ps.evp << 2) & 0x7Cu)) | (ps.evp & 0xFFFFFC00u)),
                         "r"(1u << ((ps.evp >> 5) & 31u)) : "memory");
         if (ps.last_p1 > f.W) break;  // otherwise every pending event lay inside this window and has just been applied
         const u32 pre = warp_scan_add(1u + geom_gap(dp.next_rk(dv), f.inv));
@@ -1193,9 +1235,9 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     f.col = keep(smem_addr(st.s));
     f.warp_cols = keep(smem_addr(a.sst + (threadIdx.x & ~31u)));
     f.thr = keep(smem_addr(a.blob + nv.off_thr));
-    f.rec = keep(smem_addr(a.blob + nv.off_rec));
+    f.rec = keep(smem_addr(a.blob + nv.off_rec16));
     f.thr_stride = keep((u32)nv.tsq_stride * 16u);
-    f.rec_stride = keep((u32)nv.fmax * 8u);
+    f.rec_stride = keep((u32)nv.fmax * 16u);
     f.shist = keep(smem_addr(a.shist));
     f.n = keep((u32)nv.n);
     f.W = keep((u32)nv.n * 32u);
@@ -1247,7 +1289,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
     SsdCount cnt{active ? ssd_bucket(sp, a.s_tgt, st) : 0, 0u};
     int t = 0;
     if constexpr (MODE == PBN_DRAW_PHILOX && !HAS_ENV && FULL && NET == PBN_NET_PRED && TQ > 0) {
-        if (flips && sp.smem_hist && sp.fast_t0 >= 0) t = ssd_loop_pred_static<TQ>(a, st, d, dp, ps, cnt);
+        if (flips && sp.smem_hist && sp.fast_t0 >= 0 && nv.off_rec16) t = ssd_loop_pred_static<TQ>(a, st, d, dp, ps, cnt);
     }
     if constexpr (MODE == PBN_DRAW_PHILOX && !HAS_ENV && FULL) {
         // STATIC path: one Philox block of the update stream per two iterations, words used in stream order
@@ -1380,13 +1422,14 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
                                                    long long chains, long long env0, int iters,
                                                    unsigned long long *hist) {
     unsigned char *blob = smem_raw;
-    unsigned char *img = smem_raw + nv.blob_bytes;
+    const int bb = HAS_ENV ? nv.blob_bytes : nv.blob_fast_bytes;  // the all-attracting paths also stage the 16-byte records
+    unsigned char *img = smem_raw + bb;
     const int img_bytes = HAS_ENV ? ev.img_bytes : 0;
     u32 *s_tgt = reinterpret_cast<u32 *>(img + img_bytes);
     u32 *shist = s_tgt + 32;
     const int nb = 1 << sp.g;
-    u32 *sst = shist + (sp.smem_hist ? nb : 0);
-    stage(blob, nv.blob, nv.blob_bytes);
+    u32 *sst = align_cols(shist + (sp.smem_hist ? nb : 0), nv.w32);
+    stage(blob, nv.blob, bb);
     if (HAS_ENV) stage(img, ev.img, ev.img_bytes);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -1578,7 +1621,7 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
         return PBN_OK;
     }
     const unsigned grid = (unsigned)((B + block - 1) / block);
-    const size_t smem = (size_t)nv.blob_bytes + (size_t)2 * nv.w32 * block * 4;
+    const size_t smem = (size_t)(sync ? nv.blob_bytes : nv.blob_fast_bytes) + col_align_bytes(nv.w32) + (size_t)2 * nv.w32 * PBN_BLOCK * 4;
 #define CALL(NK, MD, TQ)                                                           \
     if (int rc = set_smem(k_rollout<NK, MD, TQ>, smem)) return rc;                 \
     k_rollout<NK, MD, TQ><<<grid, block, smem, s>>>(nv, dv, state, B, env0, steps, sync)
@@ -1752,7 +1795,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     if (env) ev = env->v;
     // windowed step-until-attractor path: flip masks of `win` iterations per warp, 2 KB per warp (networks up to 256 nodes)
     sp.win = (env && draws->mode == PBN_DRAW_PHILOX && !ev.force && nv.w32 <= 8) ? (16 / nv.w32 > 2 ? 16 / nv.w32 : 2) : 0;
-    const size_t smem = (size_t)nv.blob_bytes + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + (size_t)nv.w32 * block * 4 +
+    const size_t smem = (size_t)(env ? nv.blob_bytes : nv.blob_fast_bytes) + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + col_align_bytes(nv.w32) + (size_t)nv.w32 * PBN_BLOCK * 4 +
                         (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4;
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                                                  \

@@ -27,8 +27,10 @@ struct NetView {
     int kind, n, first, w32;
     int ts, fmax;
     int tsq_stride;  // quads per threshold row: odd, so that divergent LDS.128 reads spread over all 8 bank groups
-    int blob_bytes;
+    int blob_bytes;       // staged by every kernel: the image without the fast-path records
+    int blob_fast_bytes;  // image including the 16-byte predictor records (fast asynchronous paths), == blob_bytes when absent
     int off_thr, off_rec, off_node, off_in;
+    int off_rec16;        // 0: no 16-byte records
     const unsigned char *blob;  // device
     const u32 *thr_dev;         // TT: non-null when the threshold table is read from global memory instead of the staged image
     // float64 side tables for replay mode (device, reference form)

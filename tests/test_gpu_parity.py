@@ -231,6 +231,24 @@ def test_threshold_row_layouts(eng, fmax):
     assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist) and np.array_equal(_state_np(sim), ost)
 
 
+@pytest.mark.parametrize("n,fmax", [(200, 12), (250, 5), (33, 3), (129, 7)])
+def test_fast_record_paths(eng, n, fmax):
+    """The fast asynchronous paths read 16-byte predictor records from aligned state columns (1..8 words per column);
+    networks whose records exceed 32 KB (200 nodes x 12 predictors) take the generic path.  Both against the oracle."""
+    net, onet = _random_predictor_net(eng, n, fmax, seed=n + fmax)
+    B, seed = 300, 5
+    sim = eng.engine.Simulator(net, B, seed=seed, env0=64)
+    sim.rand_state()
+    ost = orc.rand_state(onet, B, orc.Draws(seed=seed, epoch=0), env0=64)
+    sim.rollout(400)
+    orc.rollout(onet, ost, 400, orc.Draws(seed=seed, epoch=1), env0=64)
+    assert np.array_equal(_state_np(sim), ost)
+    tgt = np.arange(n - 8, n - 2, dtype=np.int32) if (n - 8) // 32 == (n - 3) // 32 else np.arange(0, 6, dtype=np.int32)
+    hist = sim.ssd(41, 0.01, tgt)
+    ohist = orc.ssd(onet, None, ost, 41, 0.01, tgt, orc.Draws(seed=seed, epoch=2), env0=64)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist) and np.array_equal(_state_np(sim), ost)
+
+
 @pytest.mark.parametrize("which", ["28_15_median", "100_5_kmeans", "200_5_kmeans", "70_5_kmeans", "tt"])
 @pytest.mark.parametrize("sync", [False, True])
 def test_philox_rollout_matches_oracle(eng, which, sync):
