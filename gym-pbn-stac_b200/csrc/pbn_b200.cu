@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -310,7 +312,7 @@ struct SsdFast {
     u32 shist;      // shared address of the block histogram
     u32 n, W;
     u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
-    float inv;
+    float inv, gdelta;
 };
 
 // 16 * #{k : t[k] <= r} for an ascending quad of thresholds (cumulative COD rows are ascending, so the predicates are
@@ -1097,6 +1099,7 @@ struct SsdParams {
     int fast_t0;    // >= 0: the targets are nodes t0, t0+1, .. t0+g-1 inside one state word (bucket = bit-reversed field)
     int win;        // iterations per window of the step-until-attractor path (0 = iteration by iteration)
     float inv;      // 1/log2(1-p) <= 0; a value > 0 means flips disabled (p == 0)
+    float gdelta;   // margin of the lg2.approx shortcut of the gap draw (geom_gap_approx); >= 0.5: shortcut off
     double p;
     short tgt[24];
 };
@@ -1216,7 +1219,11 @@ __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &p
                      :: "r"(ps.evp), "r"(f.W), "r"((f.warp_cols | ((ps.evp << 2) & 0x7Cu)) | (ps.evp & 0xFFFFFC00u)),
                         "r"(1u << ((ps.evp >> 5) & 31u)) : "memory");
         if (ps.last_p1 > f.W) break;  // otherwise every pending event lay inside this window and has just been applied
-        const u32 pre = warp_scan_add(1u + geom_gap(dp.next_rk(dv), f.inv));
+        const u32 word = dp.next_rk(dv);
+        bool ok;
+        u32 gap = geom_gap_approx(word, f.inv, f.gdelta, &ok);
+        if (!ok) gap = geom_gap(word, f.inv);  // within the margin of an integer (or shortcut off): the defining polynomial
+        const u32 pre = warp_scan_add(1u + gap);
         ps.evp = ps.last_p1 - 1u + pre;
         ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
     }
@@ -1245,6 +1252,7 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     f.b_sh = keep((u32)a.sp.fast_t0 & 31u);
     f.b_up = keep(32u - (u32)a.sp.g);
     f.inv = a.sp.inv;
+    f.gdelta = a.sp.gdelta;
     u32 ublk = 0;
     int t = 0;
     u32 cur = (u32)cnt.cur, run = cnt.run;
@@ -1760,6 +1768,51 @@ extern "C" int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int
     return PBN_OK;
 }
 
+// Exhaustive check of the gap shortcut for one value of inv: the gap depends on the top 23 bits of the draw only.
+__global__ void __launch_bounds__(256) k_geom_verify(float inv, float dlt, unsigned int *bad, unsigned int *taken) {
+    const u32 r = ((u32)blockIdx.x * 256u + threadIdx.x) << 9;
+    bool ok;
+    const u32 a = geom_gap_approx(r, inv, dlt, &ok);
+    if (ok) {
+        if (a != geom_gap(r, inv)) atomicAdd(bad, 1u);
+    } else {
+        atomicAdd(taken, 1u);  // inputs that take the polynomial anyway
+    }
+}
+// Margin for inv, or 1.0 (shortcut off) when it would not pay or the exhaustive comparison finds a disagreement.  Verified once
+// per value of inv and device (blocking, ~0.1 ms); during stream capture an unverified value runs without the shortcut.
+static float geom_shortcut_delta(float inv, cudaStream_t s) {
+    static std::mutex mu;
+    static std::map<std::pair<int, u32>, float> cache;
+    if (!(inv < 0.f)) return 1.0f;
+    // |lg2.approx - log2| <= 2^-22 * max(1, |log2 u|) (documented), |log2 u| <= 24; the polynomial is within 2e-7 of log2 on
+    // the reduced interval; twice the sum, scaled by |inv|
+    const float dlt = -inv * 2.0f * (24.0f * 2.3841858e-7f + 2e-7f);
+    if (!(dlt < 0.05f)) return 1.0f;  // more than ~10 % of the draws would fall back: not worth it
+    int dev = 0;
+    cudaGetDevice(&dev);
+    u32 bits;
+    memcpy(&bits, &inv, 4);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, bits});
+    if (it != cache.end()) return it->second;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return 1.0f;
+    unsigned int *d = nullptr, h[2] = {1u, 0u};
+    float res = 1.0f;
+    if (cudaMalloc(&d, 8) == cudaSuccess) {
+        if (cudaMemsetAsync(d, 0, 8, s) == cudaSuccess) {
+            k_geom_verify<<<(1u << 23) / 256u, 256, 0, s>>>(inv, dlt, d, d + 1);
+            if (cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess &&
+                h[0] == 0u)
+                res = dlt;
+        }
+        cudaFree(d);
+    }
+    cache[{dev, bits}] = res;
+    return res;
+}
+
 extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chains, int64_t env0, int64_t iters,
                        double p, const int32_t *tgt, int32_t g, uint64_t *hist, const PbnDraws *draws, void *stream) {
     if (!net || !state || !tgt || !hist || chains < 0 || iters < 0) return fail(PBN_ERR_ARG, "bad argument");
@@ -1776,6 +1829,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     SsdParams sp;
     sp.g = g; sp.p = p; sp.smem_hist = g <= 12;
     sp.inv = p <= 0 ? 1.0f : (p >= 1 ? 0.0f : (float)(1.0 / std::log2(1.0 - p)));
+    sp.gdelta = 1.0f;
     memset(sp.tgt, 0, sizeof sp.tgt);
     for (int k = 0; k < g; k++) {
         if (tgt[k] < 0 || tgt[k] >= nv.n) return fail(PBN_ERR_ARG, "target node out of range");
@@ -1798,6 +1852,8 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     const size_t smem = (size_t)(env ? nv.blob_bytes : nv.blob_fast_bytes) + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + col_align_bytes(nv.w32) + (size_t)nv.w32 * PBN_BLOCK * 4 +
                         (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!env && nv.kind == PBN_NET_PRED && draws->mode == PBN_DRAW_PHILOX && sp.smem_hist && sp.fast_t0 >= 0 && nv.off_rec16)
+        sp.gdelta = geom_shortcut_delta(sp.inv, s);  // the static predictor path draws its gaps with the verified shortcut
 #define CALL(NK, MD, TQ)                                                                                  \
     if (env) {                                                                                            \
         if (int rc = set_smem(k_ssd<NK, MD, TQ, true>, smem)) return rc;                                  \

@@ -224,6 +224,21 @@ __device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
     return (u32)g;                              // g >= 0: truncation
 }
 
+// Shortcut for the same gap: hardware lg2.approx instead of the polynomial.  It is taken only when the result is provably the
+// polynomial's: the two logarithms differ by less than `dlt` after scaling, so whenever the approximate g lies at least dlt
+// away from an integer both truncate to the same gap; otherwise *ok is false and the caller evaluates geom_gap.  The host
+// does not rely on the documented error bound of lg2.approx alone: before a value of `inv` is used with the shortcut,
+// k_geom_verify compares the two functions on all 2^23 possible inputs (pbn_b200.cu: geom_shortcut_delta).
+__device__ __forceinline__ u32 geom_gap_approx(u32 r, float inv, float dlt, bool *ok) {
+    const float u = __fmul_rn(__fadd_rn((float)(r >> 9), 0.5f), 1.0f / 8388608.0f);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    const float g = __fmul_rn(lg, inv);
+    const float fr = __fsub_rn(g, truncf(g));  // exact; 0 for g >= 2^23 (then never ok)
+    *ok = fabsf(__fsub_rn(fr, 0.5f)) < __fsub_rn(0.5f, dlt);
+    return (u32)g;
+}
+
 // ----------------------------------------------------------------------------------------------- state column
 #define PBN_BLOCK 256  // every kernel runs 256-thread blocks, so a column's word stride is a compile-time constant
 struct Col {
