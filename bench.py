@@ -257,6 +257,10 @@ def run_gpu(args):
             "frac": (achieved / alu_peak) if achieved else None,
             "peak_source": "pbn_issue_peak(0): dependency-free LOP3+IADD3 chains, measured in this run",
             "thread_inst_per_iter": tipi, "inst_source": ipi.get("source"),
+            # the same fraction with the iteration priced at SURVEY §8d's fixed estimate (150 thread-instr per asynchronous
+            # micro-step): unlike `frac` (issue utilisation of the instructions actually executed) it rises when the kernel
+            # gets leaner
+            "frac_at_survey_150_instr": 150.0 * per_launch_iters / t_kernel / alu_peak,
             "kernel_ms": t_kernel * 1e3,
             "iters_per_s_kernel": per_launch_iters / t_kernel,
             "philox_blocks_per_s": 0.75 * per_launch_iters / t_kernel,  # 2 update draws + ~1 gap draw per iteration

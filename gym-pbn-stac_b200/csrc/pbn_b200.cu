@@ -1813,6 +1813,23 @@ static float geom_shortcut_delta(float inv, cudaStream_t s) {
     return res;
 }
 
+extern "C" int pbn_geom_shortcut_check(double p, float *delta, uint32_t *disagree, uint32_t *fallback) {
+    if (!(p > 0.0 && p < 1.0) || !delta || !disagree || !fallback) return fail(PBN_ERR_ARG, "bad argument");
+    const float inv = (float)(1.0 / std::log2(1.0 - p));
+    *delta = geom_shortcut_delta(inv, nullptr);
+    const float dlt = -inv * 2.0f * (24.0f * 2.3841858e-7f + 2e-7f);  // the margin the shortcut would use
+    unsigned int *d = nullptr, h[2] = {0u, 0u};
+    CK(cudaMalloc(&d, 8));
+    cudaMemset(d, 0, 8);
+    k_geom_verify<<<(1u << 23) / 256u, 256>>>(inv, dlt < 0.5f ? dlt : 0.5f, d, d + 1);
+    cudaError_t e = cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CK(e);
+    *disagree = h[0];
+    *fallback = h[1];
+    return PBN_OK;
+}
+
 extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chains, int64_t env0, int64_t iters,
                        double p, const int32_t *tgt, int32_t g, uint64_t *hist, const PbnDraws *draws, void *stream) {
     if (!net || !state || !tgt || !hist || chains < 0 || iters < 0) return fail(PBN_ERR_ARG, "bad argument");

@@ -86,6 +86,7 @@ EXPORTS = {
                                     C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "pbn_fit_eval_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "pbn_issue_peak": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+    "pbn_geom_shortcut_check": (C.c_int, [C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pbn_last_error": (C.c_char_p, []),
     "pbn_version": (C.c_char_p, []),
 }

@@ -249,6 +249,13 @@ int pbn_fetch_step_host(const int32_t *reward, const uint8_t *terminated, const 
    IADD) to see the issue rate of each class.  Writes elapsed ms and the number of thread-level operations executed. */
 int pbn_issue_peak(int32_t kind, int64_t iters, float *ms_out, double *ops_out);
 
+/* Test hook of the SSD kernel's gap draw (utils/eval.py:92-95 flips each node with probability p; the kernels draw the
+   geometric gaps between flips instead).  The gap is DEFINED by a fixed single-precision polynomial for log2 (the oracle's
+   orc_geom); the fast path takes the hardware lg2.approx when the result lies further than `delta` from an integer.  This
+   call runs both on all 2^23 possible inputs for flip probability p and reports the margin in use (1.0 = shortcut off),
+   how many inputs disagreed where the shortcut would have been taken (must be 0), and how many inputs fall back. */
+int pbn_geom_shortcut_check(double p, float *delta, uint32_t *disagree, uint32_t *fallback);
+
 const char *pbn_last_error(void);
 const char *pbn_version(void);
 

@@ -670,3 +670,18 @@ def test_sync_sliced_split_invariance_and_errors(eng):
     net28, _ = _nets(eng, "28_15_median")  # 15 predictors per node: not supported by the sliced kernel
     with pytest.raises(eng.abi.PbnError):
         eng.engine.Simulator(net28, 64, seed=8).rollout(1, sync="sliced")
+
+
+@pytest.mark.parametrize("p", [0.01, 0.02, 0.001, 0.3, 1e-5])
+def test_gap_shortcut_is_exact(eng, p):
+    """The lg2.approx shortcut of the SSD gap draw against the defining polynomial on ALL 2^23 inputs: no disagreement where
+    it is taken; on for the usual flip probabilities (few inputs fall back), off when the margin would be too wide."""
+    import ctypes as C
+
+    delta, bad, fb = C.c_float(), C.c_uint32(), C.c_uint32()
+    eng.abi.check(eng.abi.lib().pbn_geom_shortcut_check(p, C.byref(delta), C.byref(bad), C.byref(fb)))
+    assert bad.value == 0
+    if p >= 0.001:
+        assert delta.value < 0.05 and fb.value < 0.1 * 2**23
+    if p == 1e-5:
+        assert delta.value == 1.0

@@ -61,6 +61,8 @@ def main():
         out += ["", f"* warp instructions per warp-iteration: **{wi / (args.iters_per_launch / 32):.1f}**",
                 f"* thread instructions per SSD iteration: **{ti / args.iters_per_launch:.1f}**",
                 f"* DRAM bytes per launch (read+write): {dram:.4g}", ""]
+        if wi != wi:  # a launch whose counters ncu could not collect (nan): keep the previous one
+            continue
         last = {"thread_inst_per_iter": ti / args.iters_per_launch, "warp_inst_per_warp_iter": wi / (args.iters_per_launch / 32),
                 "dram_bytes_per_launch": dram, "issue_active_pct": float(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
                 "source": f"profiles/{args.tag}_ssd_ncu_summary.md (ncu --set full, {args.command})"}
