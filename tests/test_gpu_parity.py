@@ -685,3 +685,22 @@ def test_gap_shortcut_is_exact(eng, p):
         assert delta.value < 0.05 and fb.value < 0.1 * 2**23
     if p == 1e-5:
         assert delta.value == 1.0
+
+
+def test_ssd_histogram_host_matches_oracle(eng):
+    """ssd_histogram_host (the end-to-end call bench.py times; host states in, host histogram out) on several waves of
+    blocks: the histogram equals the oracle's, from pinned and from pageable start states."""
+    from gym_PBN.utils.eval import ssd_histogram_host
+
+    net, onet = _nets(eng, "100_5_kmeans")
+    wave = torch.cuda.get_device_properties(0).multi_processor_count * 4 * 256
+    chains, iters, seed, env0 = 2 * wave + 4096, 3, 17, 64
+    rng = np.random.default_rng(0)
+    st = rng.integers(0, 2, size=(chains, 100)).astype(np.uint8)
+    tgt = np.arange(7, dtype=np.int32)
+    h_pinned = ssd_histogram_host(net, torch.from_numpy(st).pin_memory(), iters, 0.01, tgt, seed=seed, env0=env0)
+    h_plain = ssd_histogram_host(net, st, iters, 0.01, tgt, seed=seed, env0=env0)
+    ost = st.copy()
+    ohist = orc.ssd(onet, None, ost, iters, 0.01, tgt, orc.Draws(seed=seed, epoch=0), env0=env0)
+    assert np.array_equal(h_pinned.astype(np.uint64), ohist) and np.array_equal(h_plain, h_pinned)
+    assert int(h_pinned.sum()) == chains * iters
