@@ -103,6 +103,8 @@ extern "C" int pbn_net_create(const PbnNetDesc *d, PbnNet **out) {
         for (int i = 0; i < n; i++) {
             const int q0 = d->pr_off[i], f = d->pr_off[i + 1] - q0;
             for (int k = 0; k < row; k++) thr[i * row + k] = 0x80000000u;
+            for (int k = 1; k < f; k++)  // the threshold search (count / select chain) relies on ascending rows
+                if (!(d->pr_cum[q0 + k] >= d->pr_cum[q0 + k - 1])) { delete net; return fail(PBN_ERR_ARG, "cumulative COD must be non-decreasing (negative COD?)"); }
             for (int k = 0; k < ts; k++) {
                 const u32 t = (k < f - 1) ? thr31(d->pr_cum[q0 + k] / d->pr_codsum[i]) : 0x80000000u;
                 thr[i * row + lead * 4 + k] = t;
@@ -312,7 +314,7 @@ struct SsdFast {
     u32 shist;      // shared address of the block histogram
     u32 n, W;
     u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
-    float inv, gdelta;
+    float inv, gdelta;  // gdelta: 0.5 - margin of the gap shortcut
 };
 
 // 16 * #{k : t[k] <= r} for an ascending quad of thresholds (cumulative COD rows are ascending, so the predicates are
@@ -1252,7 +1254,7 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     f.b_sh = keep((u32)a.sp.fast_t0 & 31u);
     f.b_up = keep(32u - (u32)a.sp.g);
     f.inv = a.sp.inv;
-    f.gdelta = a.sp.gdelta;
+    f.gdelta = 0.5f - a.sp.gdelta;  // the shortcut compares against 0.5 - margin (negative: never taken)
     u32 ublk = 0;
     int t = 0;
     u32 cur = (u32)cnt.cur, run = cnt.run;
@@ -1772,7 +1774,7 @@ extern "C" int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int
 __global__ void __launch_bounds__(256) k_geom_verify(float inv, float dlt, unsigned int *bad, unsigned int *taken) {
     const u32 r = ((u32)blockIdx.x * 256u + threadIdx.x) << 9;
     bool ok;
-    const u32 a = geom_gap_approx(r, inv, dlt, &ok);
+    const u32 a = geom_gap_approx(r, inv, 0.5f - dlt, &ok);
     if (ok) {
         if (a != geom_gap(r, inv)) atomicAdd(bad, 1u);
     } else {

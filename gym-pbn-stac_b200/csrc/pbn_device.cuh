@@ -217,25 +217,28 @@ __device__ __forceinline__ float log2f_poly(float x) {
     p = __fmaf_rn(p, t, 1.442695022e+00f);
     return __fmaf_rn(p, t, (float)e);
 }
+// u = (k + 0.5) * 2^-23 for the top 23 bits k of the draw; one fma: every intermediate is exact, so this is the oracle's
+// (k + 0.5f) * 2^-23 bit for bit
+__device__ __forceinline__ float gap_uniform(u32 r) { return __fmaf_rn((float)(r >> 9), 1.0f / 8388608.0f, 1.0f / 16777216.0f); }
 __device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
-    float u = __fmul_rn(__fadd_rn((float)(r >> 9), 0.5f), 1.0f / 8388608.0f);
+    float u = gap_uniform(r);
     float g = __fmul_rn(log2f_poly(u), inv);
     if (!(g < 67108864.0f)) return 67108864u;  // gaps are capped at 2^26 so a warp prefix sum of 32 gaps fits 32 bits
     return (u32)g;                              // g >= 0: truncation
 }
 
 // Shortcut for the same gap: hardware lg2.approx instead of the polynomial.  It is taken only when the result is provably the
-// polynomial's: the two logarithms differ by less than `dlt` after scaling, so whenever the approximate g lies at least dlt
+// polynomial's: the two logarithms differ by less than a margin dlt after scaling, so whenever the approximate g lies at least dlt
 // away from an integer both truncate to the same gap; otherwise *ok is false and the caller evaluates geom_gap.  The host
 // does not rely on the documented error bound of lg2.approx alone: before a value of `inv` is used with the shortcut,
 // k_geom_verify compares the two functions on all 2^23 possible inputs (pbn_b200.cu: geom_shortcut_delta).
-__device__ __forceinline__ u32 geom_gap_approx(u32 r, float inv, float dlt, bool *ok) {
-    const float u = __fmul_rn(__fadd_rn((float)(r >> 9), 0.5f), 1.0f / 8388608.0f);
+__device__ __forceinline__ u32 geom_gap_approx(u32 r, float inv, float half_minus_dlt, bool *ok) {
+    const float u = gap_uniform(r);
     float lg;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
     const float g = __fmul_rn(lg, inv);
     const float fr = __fsub_rn(g, truncf(g));  // exact; 0 for g >= 2^23 (then never ok)
-    *ok = fabsf(__fsub_rn(fr, 0.5f)) < __fsub_rn(0.5f, dlt);
+    *ok = fabsf(__fsub_rn(fr, 0.5f)) < half_minus_dlt;  // the caller passes 0.5 - dlt
     return (u32)g;
 }
 

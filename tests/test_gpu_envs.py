@@ -284,6 +284,11 @@ def test_abi_error_paths():
         s2 = engine.Simulator(tt, 4)
         s2.env_step(engine.EnvImage(tt, abi.ENV_PBN_SD, attractors=[[(0, 0)]], targets=[(0, 1)]), torch.zeros((4, 1), dtype=torch.int32))
     assert b"" == b"" and abi.lib().pbn_last_error() is not None
+    with pytest.raises(ValueError):  # a negative COD would make a cumulative row descend
+        spec = compiler.load_bittner("28_15_median")
+        spec.arrays["pr_cum"] = spec.arrays["pr_cum"].copy()
+        spec.arrays["pr_cum"][1] = spec.arrays["pr_cum"][0] - 0.5
+        engine.Network(spec)
     with pytest.raises(abi.PbnError):  # predictor networks are limited to 256 nodes
         spec = compiler.load_bittner("28_15_median")
         spec.n = 300
