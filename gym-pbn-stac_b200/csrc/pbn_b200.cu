@@ -1159,8 +1159,16 @@ struct SsdPerturb {
     u32 last_p1;  // (position of the last generated event) + 1, relative to the window start
 };
 
+// gap draw of the generic paths: the verified shortcut when the launch carries a margin (hmd = 0.5 - margin > 0)
+__device__ __forceinline__ u32 ssd_gap(u32 word, float inv, float hmd) {
+    bool ok;
+    u32 gap = geom_gap_approx(word, inv, hmd, &ok);
+    if (!ok) gap = geom_gap(word, inv);
+    return gap;
+}
+
 template <bool FULL>
-__device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, char *warp_cols, u32 W, float inv, u32 nvalid) {
+__device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, char *warp_cols, u32 W, float inv, float hmd, u32 nvalid) {
     for (;;) {
         if (ps.evp < W) {
             const u32 tl = ps.evp & 31u;
@@ -1170,7 +1178,7 @@ __device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX
             ps.evp = 0xFFFFFFFFu;
         }
         if (ps.last_p1 > W) break;  // the last generated event lies beyond this window
-        const u32 pre = warp_scan_add(1u + geom_gap(dp.next(), inv));
+        const u32 pre = warp_scan_add(1u + ssd_gap(dp.next(), inv, hmd));
         ps.evp = ps.last_p1 - 1u + pre;
         ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
     }
@@ -1182,7 +1190,7 @@ __device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX
 // The same renewal process, with the events of one iteration recorded in a flip mask [w32][32] (word w of chain tl at
 // buf[w*32 + tl]) instead of being applied: the windowed loop below draws the masks of several iterations ahead.
 template <bool FULL>
-__device__ __forceinline__ void ssd_perturb_buf(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, u32 *buf, u32 W, float inv, u32 nvalid) {
+__device__ __forceinline__ void ssd_perturb_buf(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, u32 *buf, u32 W, float inv, float hmd, u32 nvalid) {
     for (;;) {
         if (ps.evp < W) {
             const u32 tl = ps.evp & 31u;
@@ -1190,7 +1198,7 @@ __device__ __forceinline__ void ssd_perturb_buf(SsdPerturb &ps, Draw<PBN_DRAW_PH
             ps.evp = 0xFFFFFFFFu;
         }
         if (ps.last_p1 > W) break;
-        const u32 pre = warp_scan_add(1u + geom_gap(dp.next(), inv));
+        const u32 pre = warp_scan_add(1u + ssd_gap(dp.next(), inv, hmd));
         ps.evp = ps.last_p1 - 1u + pre;
         ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
     }
@@ -1293,6 +1301,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
     const bool active = FULL || lane < a.nvalid;
     const u32 n = (u32)nv.n, W = n * 32u;
     const float inv = sp.inv;
+    const float hmd = 0.5f - sp.gdelta;  // gap shortcut: 0.5 - margin (negative: never taken)
     const bool flips = inv <= 0.f;
     SsdPerturb ps{0xFFFFFFFFu, 0u};
     char *warp_cols = reinterpret_cast<char *>(a.sst + (threadIdx.x & ~31u));
@@ -1309,11 +1318,11 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
             philox4x32_10(ublk, d.c1, d.c2, d.c3, d.k0, d.k1, x0, x1, x2, x3);
             ublk++;
             ssd_count(cnt, a, st);
-            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, 32u);
+            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, hmd, 32u);
             micro_step_words<NET, TQ>(nv, a.blob, st, x0, x1, d);
             __syncwarp();  // updates land before the next iteration's cross-lane flips
             ssd_count(cnt, a, st);
-            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, 32u);
+            if (flips) ssd_perturb<true>(ps, dp, warp_cols, W, inv, hmd, 32u);
             micro_step_words<NET, TQ>(nv, a.blob, st, x2, x3, d);
             __syncwarp();
         }
@@ -1335,7 +1344,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                 for (int k = 0; k < kk; k++) {
                     for (int w = 0; w < w32; w++) fb[(k * w32 + w) * 32 + lane] = 0u;
                     __syncwarp();
-                    if (flips) ssd_perturb_buf<FULL>(ps, dp, fb + k * w32 * 32, W, inv, a.nvalid);
+                    if (flips) ssd_perturb_buf<FULL>(ps, dp, fb + k * w32 * 32, W, inv, hmd, a.nvalid);
                 }
                 __syncwarp();
                 int k = 0, in = 0;
@@ -1402,7 +1411,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                 for (u32 j = 0; j < n; j++)
                     if (d.dbl() < sp.p) st.flip(j);  // np.random.rand(N) < p ; flipNode(j)  (eval.py:92-95)
         } else {
-            if (flips) ssd_perturb<FULL>(ps, dp, warp_cols, W, inv, a.nvalid);
+            if (flips) ssd_perturb<FULL>(ps, dp, warp_cols, W, inv, hmd, a.nvalid);
         }
         if (active) {
             micro_step<NET, MODE, TQ>(nv, a.blob, st, d);  // env.step(0): pbn_target.py:269-271
@@ -1871,8 +1880,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     const size_t smem = (size_t)(env ? nv.blob_bytes : nv.blob_fast_bytes) + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + col_align_bytes(nv.w32) + (size_t)nv.w32 * PBN_BLOCK * 4 +
                         (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!env && nv.kind == PBN_NET_PRED && draws->mode == PBN_DRAW_PHILOX && sp.smem_hist && sp.fast_t0 >= 0 && nv.off_rec16)
-        sp.gdelta = geom_shortcut_delta(sp.inv, s);  // the static predictor path draws its gaps with the verified shortcut
+    if (draws->mode == PBN_DRAW_PHILOX) sp.gdelta = geom_shortcut_delta(sp.inv, s);  // gaps are drawn with the verified shortcut
 #define CALL(NK, MD, TQ)                                                                                  \
     if (env) {                                                                                            \
         if (int rc = set_smem(k_ssd<NK, MD, TQ, true>, smem)) return rc;                                  \
