@@ -1460,7 +1460,6 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long e = (long long)blockIdx.x * PBN_BLOCK + threadIdx.x;
     const int w32 = nv.w32;
-    const u32 n = (u32)nv.n;
     Col st{sst + threadIdx.x};
     const int win = sp.win;
     u32 *flipbuf = (HAS_ENV && win > 0) ? sst + w32 * PBN_BLOCK : nullptr;
