@@ -914,7 +914,7 @@ __device__ __forceinline__ int coop_run_w1(const NetView &nv, const EnvView &ev,
         const u32 r = wb >> 1;
         const uint4 *thr = thr_rows + i * nv.tsq_stride;
         u32 j;
-        if (TQ == 1) {
+        if constexpr (TQ == 1) {
             const uint4 t = thr[0];
             j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
         } else {
