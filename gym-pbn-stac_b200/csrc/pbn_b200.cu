@@ -359,6 +359,8 @@ __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb
     sts_u32(wa_addr, (old & ~m) | (__funnelshift_l(0u, v, i) & m));  // bit i <- LUT bit idx
 }
 
+#include "pbn_coop.cuh"
+
 static DrawView make_draws(const PbnDraws *d) {
     DrawView v;
     v.mode = d->mode; v.epoch = d->epoch;
@@ -789,165 +791,29 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 // contiguous range of envs and its threads pull the next env from a block-local counter the moment they finish one, in a
 // flat loop whose every trip is "one attractor test + at most one update" for every lane — lanes never wait at the end
 // of an inner loop.  An env's result does not depend on which thread ran it (its Philox stream is keyed by its id).
-// Straggler mode of the step-until-attractor kernel (predictor networks, Philox draws).  When a block's queue is empty and
-// only a few lanes of a warp still hold an env, those envs are finished ONE AT A TIME by the whole warp: the lanes draw 32
-// Philox blocks of the env's update stream at once (64 updates' worth of words, fetched by shuffle), test one attractor cube
-// each, and execute the state-dependent part of the update in lockstep on the env's shared-memory column.  A lone lane in the
-// ordinary loop spends ~1600 cycles per update on a fully dependent instruction chain; here an update is ~200 cycles, which is
-// what bounds a launch whose slowest env needs thousands of updates (the reference's loop is unbounded, pbn_target.py:270-271).
-// The env's words are the same ones the ordinary loop would have used (update k takes words 2k, 2k+1), so results are identical.
+// Straggler mode of the step-until-attractor kernel (predictor networks, Philox draws): when a block's queue is empty and
+// only a few lanes of a warp still hold an env, the warp stops running them as lone lanes (a lone lane's update is a
+// ~1 500-cycle dependent chain) and splits into 1, 2, 4 or 8 groups of 32/k lanes, each finishing one env with the draw
+// half of the updates spread over its lanes and the state half pipelined (pbn_coop.cuh: coop_steps).  The env's words are
+// the ones the ordinary loop would have used (update k takes words 2k, 2k+1), so results are identical.
 #ifndef PBN_COOP_MAX
 #define PBN_COOP_MAX 8   // live envs per warp at which straggler mode takes over (groups of 32 / 8 = 4 lanes)
 #endif
-// In a small batch (at most PBN_COOP_SMALL_BATCH envs per block, i.e. one or two per thread) the launch is as long as its
-// slowest env and the SMs are mostly idle, so the mode starts early; in a large batch the SM is issue-bound and a warp
-// switches only for its last two envs.
-#ifndef PBN_COOP_SMALL_BATCH
-#define PBN_COOP_SMALL_BATCH 512
+#ifndef PBN_COOP_EXIT_AT
+#define PBN_COOP_EXIT_AT 2  // group mode, queue not empty: stopped groups at which a call returns to finalize / refill
 #endif
-#ifndef PBN_COOP_MIN_IN
-#define PBN_COOP_MIN_IN 2  // MULTI compares the pre-update observation on its first test; from the second on it is the state
-#endif
-// The warp is split into k = 1, 2, 4 or 8 groups of g = 32 / k lanes; group r finishes the env of the r-th live lane, all
-// groups at once.  Inside a group the lanes draw g Philox blocks of the env's update stream in one go (2g updates' worth of
-// words, fetched by shuffle), share out the attractor cubes, and execute the state-dependent part of the update in lockstep
-// on the env's shared-memory column (every lane of the group writes the same word with the same value and reads back at
-// least its own write, so no barrier sits on the critical path).  Returns the group's final update count.
-template <int TQ, int G>  // G = 32: the whole warp on one env (group size known at compile time); G = 0: run-time group size g
-__device__ __forceinline__ int coop_run(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
-                                        const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
-                                        bool active, int g_rt, u32 pos_base = 0u) {
-    // pos_base = updates the env's stream had served before this env.step began (0 for the env kernels, the running count
-    // of the launch for the SSD kernel): update number `in` of the step takes words 2*(pos_base + in), +1
-    const int g = G > 0 ? G : g_rt;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
-    const u32 gmask = (g == 32 ? 0xFFFFFFFFu : ((1u << g) - 1u)) << gbase;
-    const Col st{col_ptr};
-    const int w32 = nv.w32;
-    const int n_cubes = att_off[ev.n_att];
-    Draw<PBN_DRAW_PHILOX> dummy;
-    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-    int u = 0, batch = 0;
-    u32 off = 0;
-    bool running = active;
-    for (;;) {
-        // every lane runs the same instruction stream whether or not its group is still running (a finished or unused group
-        // recomputes on its column and commits nothing): no divergent regions inside the loop
-        bool hit = false;
-        for (int c0 = 0; c0 < n_cubes; c0 += g) {
-            const int c = c0 + (int)sub;
-            hit |= c < n_cubes && cube_match(cubes, c, st, w32);
-        }
-        const unsigned votes = __ballot_sync(0xFFFFFFFFu, hit);
-        running = running && in < ev.max_inner && (votes & gmask) == 0u;
-        if (!__any_sync(0xFFFFFFFFu, running)) break;
-        if (u == batch) {  // g blocks of the update stream from word 2*(pos_base + in) on (uniform inside a group)
-            const u32 a = 2u * (pos_base + (u32)in);
-            off = a & 3u;
-            philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
-            u = 0;
-            batch = (int)((4u * (u32)g - off) >> 1);
-        }
-        const u32 w = off + 2u * (u32)u;          // word index inside the batch; (w & 3) is 0 or 2
-        const bool hi_pair = (w & 2u) != 0u;
-        const u32 src = gbase + ((w >> 2) & (u32)(g - 1));
-        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, src);
-        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, src);
-        const int i = nv.first + (int)__umulhi(wa, (u32)(nv.n - nv.first));
-        const u32 v = pred_next<PBN_DRAW_PHILOX, TQ>(nv, blob, st, i, dummy, wb, true);
-        if (running) {
-            st.put(i, v);
-            in++;
-            u++;
-        }
-    }
-    return in;
-}
-
-// The same for networks of at most 32 nodes (one state word: the 28-gene Bittner set of BASELINE config 2): the state lives
-// in a REGISTER of every lane of the group for the whole run, so the attractor test, the four input gathers and the write-back
-// involve no shared-memory round trip; what is left on the dependent chain of an update is one vote, the threshold and record
-// loads.  One ballot per trip serves both the group's own test and the exit test (finished, capped and unused groups keep
-// voting "done").
-template <int TQ, int G>
-__device__ __forceinline__ int coop_run_w1(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
-                                           const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
-                                           bool active, int g_rt, u32 pos_base = 0u) {
-    const int g = G > 0 ? G : g_rt;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
-    const u32 gmask = (g == 32 ? 0xFFFFFFFFu : ((1u << g) - 1u)) << gbase;
-    // bit r*g set for every group r: after OR-folding the ballot inside the groups these bits say "group r is done"
-    const u32 heads = g == 32 ? 1u : (g == 16 ? 0x00010001u : (g == 8 ? 0x01010101u : (g == 4 ? 0x11111111u : 0x55555555u)));
-    const int n_cubes = att_off[ev.n_att];
-    const uint4 *thr_rows = reinterpret_cast<const uint4 *>(blob + nv.off_thr);
-    const uint2 *recs = reinterpret_cast<const uint2 *>(blob + nv.off_rec);
-    u32 st = *col_ptr;
-    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-    int u = 0, batch = 0;
-    u32 off = 0;
-    bool running = active;
-    for (;;) {
-        bool hit = false;
-        for (int c0 = 0; c0 < n_cubes; c0 += g) {
-            const int c = c0 + (int)sub;
-            if (c < n_cubes) hit |= (st & cubes[2 * c]) == cubes[2 * c + 1];
-        }
-        u32 b = __ballot_sync(0xFFFFFFFFu, hit || !running || in >= ev.max_inner);
-        running = running && in < ev.max_inner && (b & gmask) == 0u;
-        for (int sft = 1; sft < g; sft <<= 1) b |= b >> sft;  // OR inside each group lands on the group's lowest bit
-        if ((b & heads) == heads) break;                       // every group done
-        if (u == batch) {  // g blocks of the update stream from word 2*(pos_base + in) on (uniform inside a group)
-            const u32 a = 2u * (pos_base + (u32)in);
-            off = a & 3u;
-            philox4x32_10_rk((a >> 2) + sub, dv.epoch, (u32)env_id, (u32)((u64)env_id >> 32), dv, x0, x1, x2, x3);
-            u = 0;
-            batch = (int)((4u * (u32)g - off) >> 1);
-        }
-        const u32 w = off + 2u * (u32)u;
-        const bool hi_pair = (w & 2u) != 0u;
-        const u32 src = gbase + ((w >> 2) & (u32)(g - 1));
-        const u32 wa = __shfl_sync(0xFFFFFFFFu, hi_pair ? x2 : x0, src);
-        const u32 wb = __shfl_sync(0xFFFFFFFFu, hi_pair ? x3 : x1, src);
-        const u32 i = (u32)nv.first + __umulhi(wa, (u32)(nv.n - nv.first));
-        const u32 r = wb >> 1;
-        const uint4 *thr = thr_rows + i * nv.tsq_stride;
-        u32 j;
-        if constexpr (TQ == 1) {
-            const uint4 t = thr[0];
-            j = (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
-        } else {
-            const uint4 m = thr[0];
-            u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
-            q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
-            const uint4 t = thr[1 + q];
-            j = 4u * q + (t.x <= r) + (t.y <= r) + (t.z <= r) + (t.w <= r);
-        }
-        const uint2 rec = recs[i * nv.fmax + j];
-        const u32 idx = (((st >> (rec.x & 31u)) & 1u) << 3) | (((st >> ((rec.x >> 8) & 31u)) & 1u) << 2) |
-                        (((st >> ((rec.x >> 16) & 31u)) & 1u) << 1) | ((st >> ((rec.x >> 24) & 31u)) & 1u);
-        const u32 v = (rec.y >> idx) & 1u;
-        if (running) {
-            st = (st & ~(1u << i)) | (v << i);
-            in++;
-            u++;
-        }
-    }
-    if (active) *col_ptr = st;  // every lane of the group holds the same word
-    return in;
-}
 
 template <int NET, int MODE, int TQ>
-__global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+__global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
                                                             int *inner_steps, long long B, long long env0, long long per_block,
-                                                            VecView vx) {
+                                                            int coop_on, int grp_mode, VecView vx) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
     const int w32 = nv.w32;
+    unsigned char *coop_buf = reinterpret_cast<unsigned char *>(sst + 2 * w32 * PBN_BLOCK);  // straggler-mode staging, per warp
     __shared__ int s_next;
     __shared__ unsigned long long s_stats[6];
     stage(blob, nv.blob, nv.blob_bytes);
@@ -957,13 +823,20 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long lo = (long long)blockIdx.x * per_block;
     const long long hi = lo + per_block < B ? lo + per_block : B;
-    if (threadIdx.x == 0) s_next = PBN_BLOCK;  // the first PBN_BLOCK envs of the range are taken statically
+    // GROUP mode (predictor networks, Philox draws, real attractors): only every fourth lane owns an env — 64 per block at a
+    // time — and every env is run from its second update on by a group of 4 .. 32 lanes (pbn_coop.cuh), 8 envs per warp side
+    // by side: an update costs ~100 cycles there against ~2 500 for a lane running alone in the loop below, which then only
+    // starts and finishes env.steps.  Otherwise every lane owns an env and groups only take over a warp's last few.
+    const bool grp = MODE == PBN_DRAW_PHILOX && NET == PBN_NET_PRED && grp_mode != 0;
+    const int slots = grp ? PBN_BLOCK / 4 : PBN_BLOCK;
+    if (threadIdx.x == 0) s_next = slots;  // the first envs of the range are taken statically
     __syncthreads();
     const bool multi = ev.kind == PBN_ENV_MULTI;
+    const int coop_min_in = multi ? 2 : 1;  // MULTI tests the pre-update observation first; from its second test on, the state
     Col st{sst + threadIdx.x}, ob{sst + w32 * PBN_BLOCK + threadIdx.x};
     Draw<MODE> d;
     bool have = false;
-    long long e = 0, nxt = lo + threadIdx.x;
+    long long e = 0, nxt = !grp ? lo + threadIdx.x : ((threadIdx.x & 3) == 0 ? lo + (threadIdx.x >> 2) : hi);
     int in = 0, pend = 0;
     for (;;) {
         if (!have && nxt < hi) {
@@ -1031,47 +904,42 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step_att(NetView nv, EnvView 
             }
         }
         if constexpr (MODE == PBN_DRAW_PHILOX && NET == PBN_NET_PRED) {
-            // straggler mode: few lanes left, nothing more to pull (see coop_run)
-            const unsigned hv = (ev.n_att > 0 && !ev.force) ? __ballot_sync(0xFFFFFFFFu, have && in >= PBN_COOP_MIN_IN) : 0u;
-            if (hv != 0u && __popc(__ballot_sync(0xFFFFFFFFu, have)) <= (per_block <= PBN_COOP_SMALL_BATCH ? PBN_COOP_MAX : 2) &&
-                lo + *reinterpret_cast<volatile int *>(&s_next) >= hi) {
-                const u32 lane = threadIdx.x & 31u;
-                auto take_back = [&](int owner_lane, int v) {  // the env's owner resumes with the count the group reached
-                    if ((int)lane == owner_lane && v != in) {
+            // straggler mode: few lanes left, nothing more to pull (pbn_coop.cuh)
+            const unsigned hv = (ev.n_att > 0 && !ev.force) ? __ballot_sync(0xFFFFFFFFu, have && in >= coop_min_in) : 0u;
+            const unsigned live = __ballot_sync(0xFFFFFFFFu, have);
+            const u32 lane = threadIdx.x & 31u;
+            // the queue position is read by one lane and broadcast: the branch below runs full-mask collectives
+            int qn = 0;
+            if (lane == 0u) qn = *reinterpret_cast<volatile int *>(&s_next);
+            qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
+            const bool drained = lo + qn >= hi;
+            if (coop_on && hv != 0u && (grp || (__popc(live) <= PBN_COOP_MAX && drained))) {
+                const int nl = __popc(hv);
+                int k = 1;
+                while (k < nl) k <<= 1;                 // groups: 1, 2, 4 or 8
+                const int g = 32 / k;                   // lanes per group
+                const int grp = (int)lane / g;
+                const bool active = grp < nl;
+                const int owner = active ? (int)__fns(hv, 0u, grp + 1) : 0;  // the grp-th live lane
+                const long long eL = __shfl_sync(0xFFFFFFFFu, e, owner);
+                const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
+                u32 *colL = sst + (threadIdx.x & ~31u) + (u32)owner;
+                unsigned char *wb = coop_buf + (threadIdx.x >> 5) * coop_warp_bytes(w32);
+                // the call returns when `exit_at` groups have stopped: their owners finalize on the next trip (and, while the
+                // block's queue lasts, start the next env), the other envs come back here — in wider groups once the queue
+                // is empty, which is why the first stop ends the call then
+                const int exit_at = drained ? 1 : PBN_COOP_EXIT_AT;
+                const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g, 0u, wb, exit_at)
+                                         : coop_steps<TQ, false>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g, 0u, wb, exit_at);
+                __syncwarp();
+                for (int r = 0; r < nl; r++) {          // hand each group's count back to the lane that owns the env
+                    const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
+                    if ((int)lane == (int)__fns(hv, 0u, r + 1) && v != in) {
                         in = v;
-                        // coop_run returns only when the env is attracting or capped, so no word is drawn from `d` again:
-                        // only its position (what d.done reports) is brought up to date, not its buffered words
-                        d.blk = (2u * (u32)v + 3u) >> 2;
-                        d.have = (int)((4u - ((2u * (u32)v) & 3u)) & 3u);
+                        d.seek(dv, e, env0 + e, 2u * (u32)v, 0u);
                         if (multi)
                             for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
                     }
-                };
-                if (per_block > PBN_COOP_SMALL_BATCH) {
-                    // busy SM: the last one or two envs of the warp, one after the other, the whole warp on each
-                    for (unsigned m = hv; m != 0u; m &= m - 1u) {
-                        const int L = __ffs((int)m) - 1;
-                        const long long eL = __shfl_sync(0xFFFFFFFFu, e, L);
-                        const int inL = __shfl_sync(0xFFFFFFFFu, in, L);
-                        u32 *colL = sst + (threadIdx.x & ~31u) + (u32)L;
-                        take_back(L, (TQ > 0 && w32 == 1) ? coop_run_w1<(TQ > 0 ? TQ : 1), 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32)
-                                                      : coop_run<TQ, 32>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, true, 32));
-                    }
-                } else {
-                    const int nl = __popc(hv);
-                    int k = 1;
-                    while (k < nl) k <<= 1;                 // groups: 1, 2, 4 or 8
-                    const int g = 32 / k;                   // lanes per group
-                    const int grp = (int)lane / g;
-                    const bool active = grp < nl;
-                    const int owner = active ? (int)__fns(hv, 0u, grp + 1) : 0;  // the grp-th live lane
-                    const long long eL = __shfl_sync(0xFFFFFFFFu, e, owner);
-                    const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
-                    u32 *colL = sst + (threadIdx.x & ~31u) + (u32)owner;
-                    const int fin = (TQ > 0 && w32 == 1) ? coop_run_w1<(TQ > 0 ? TQ : 1), 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g)
-                                                         : coop_run<TQ, 0>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g);
-                    for (int r = 0; r < nl; r++)            // hand each group's count back to the lane that owns the env
-                        take_back((int)__fns(hv, 0u, r + 1), __shfl_sync(0xFFFFFFFFu, fin, r * g));
                 }
                 __syncwarp();
             }
@@ -1134,6 +1002,7 @@ struct SsdLoopArgs {
     u32 *flipbuf;  // per block: [warps][win][w32][32] words, or nullptr (no windowed path)
     int win;
     long long chain_id;  // global id of this thread's chain (Philox counter words 2, 3)
+    unsigned char *coop_buf;  // per block: [warps][coop_warp_bytes(w32)] straggler-mode staging (windowed path only)
 };
 
 // inclusive warp prefix sum; shfl.up's predicate output says whether the source lane exists, so each step is two
@@ -1384,9 +1253,10 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                             const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
                             const u32 baseL = __shfl_sync(0xFFFFFFFFu, pos - (u32)in, owner);
                             u32 *colL = a.sst + (threadIdx.x & ~31u) + (u32)owner;
-                            const int fin = (TQ > 0 && w32 == 1)
-                                                ? coop_run_w1<(TQ > 0 ? TQ : 1), 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL)
-                                                : coop_run<TQ, 0>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL);
+                            unsigned char *wb = a.coop_buf + (threadIdx.x >> 5) * coop_warp_bytes(w32);
+                            const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL, wb, 32)
+                                                     : coop_steps<TQ, false>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL, wb, 32);
+                            __syncwarp();
                             for (int r = 0; r < nl; r++) {
                                 const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
                                 if ((int)lane == (int)__fns(hv, 0u, r + 1) && v != in) {
@@ -1437,7 +1307,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
 #define PBN_SSD_MIN_BLOCKS 4
 #endif
 template <int NET, int MODE, int TQ, bool HAS_ENV>
-__global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView nv, EnvView ev, DrawView dv, SsdParams sp, u32 *state,
+__global__ void __launch_bounds__(PBN_BLOCK, HAS_ENV ? 3 : PBN_SSD_MIN_BLOCKS) k_ssd(NetView nv, EnvView ev, DrawView dv, SsdParams sp, u32 *state,
                                                    long long chains, long long env0, int iters,
                                                    unsigned long long *hist) {
     unsigned char *blob = smem_raw;
@@ -1463,6 +1333,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
     Col st{sst + threadIdx.x};
     const int win = sp.win;
     u32 *flipbuf = (HAS_ENV && win > 0) ? sst + w32 * PBN_BLOCK : nullptr;
+    unsigned char *coop_buf = flipbuf ? reinterpret_cast<unsigned char *>(flipbuf + (PBN_BLOCK / 32) * win * w32 * 32) : nullptr;
     const bool active = e < chains;
     if (active) load_state(st, state, chains, e, w32);
     __syncthreads();
@@ -1474,7 +1345,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, PBN_SSD_MIN_BLOCKS) k_ssd(NetView n
         d.init(dv, e, env0 + e);
         dp.init_perturb(dv, e, env0 + e);
         const u32 nvalid = warp_left >= 32 ? 32u : (u32)warp_left;  // lanes of this warp that own a chain
-        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid, flipbuf, win, env0 + e};
+        SsdLoopArgs a{nv, ev, sp, dv, blob, att_off, cubes, s_tgt, shist, hist, sst, iters, nvalid, flipbuf, win, env0 + e, coop_buf};
         if (nvalid == 32u) ssd_loop<NET, MODE, TQ, HAS_ENV, true>(a, st, d, dp);   // every lane owns a chain: no predication
         else ssd_loop<NET, MODE, TQ, HAS_ENV, false>(a, st, d, dp);
         if (active) {
@@ -1688,7 +1559,11 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
     const int block = block_for(B);
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const bool att = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
-    const size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
+    // two columns per env + (step-until-attractor kernel) the per-warp staging of its straggler mode
+    size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
+    const size_t coop_bytes = (size_t)(block / 32) * coop_warp_bytes(nv.w32);
+    const int coop_on = att && smem + coop_bytes <= 200 * 1024;  // images that leave no room run without the straggler mode
+    if (coop_on) smem += coop_bytes;
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(NK, MD, TQ)                                                                                          \
     if (att) {                                                                                                    \
@@ -1699,11 +1574,13 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                    \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD, TQ>, block, smem));         \
         long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
-        if (pgrid > (long long)grid) pgrid = grid;                                                                \
+        const int grp_mode = coop_on && NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && ev.n_att > 0 && !ev.force; \
+        const long long cap_grid = grp_mode ? (B + PBN_BLOCK / 4 - 1) / (PBN_BLOCK / 4) : (long long)grid;        \
+        if (pgrid > cap_grid) pgrid = cap_grid;                                                                   \
         const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
         pgrid = (B + per_block - 1) / per_block;                                                                  \
         k_env_step_att<NK, MD, TQ><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, vx); \
+                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, coop_on, grp_mode, vx); \
     } else {                                                                                                      \
         const size_t smem1 = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)nv.w32 * block * 4; /* one column per env */ \
         if (int rc = set_smem(k_env_step<NK, MD>, smem1)) return rc;                                              \
@@ -1877,7 +1754,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     // windowed step-until-attractor path: flip masks of `win` iterations per warp, 2 KB per warp (networks up to 256 nodes)
     sp.win = (env && draws->mode == PBN_DRAW_PHILOX && !ev.force && nv.w32 <= 8) ? (16 / nv.w32 > 2 ? 16 / nv.w32 : 2) : 0;
     const size_t smem = (size_t)(env ? nv.blob_bytes : nv.blob_fast_bytes) + (env ? ev.img_bytes : 0) + 128 + (sp.smem_hist ? ((size_t)4 << g) : 0) + col_align_bytes(nv.w32) + (size_t)nv.w32 * PBN_BLOCK * 4 +
-                        (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4;
+                        (size_t)(block / 32) * sp.win * nv.w32 * 32 * 4 + (sp.win ? (size_t)(block / 32) * coop_warp_bytes(nv.w32) : 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (draws->mode == PBN_DRAW_PHILOX) sp.gdelta = geom_shortcut_delta(sp.inv, s);  // gaps are drawn with the verified shortcut
 #define CALL(NK, MD, TQ)                                                                                  \
