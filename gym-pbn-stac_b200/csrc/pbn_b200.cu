@@ -47,6 +47,7 @@ struct PbnEnv {
     EnvView v;
     const PbnNet *net;
     std::vector<void *> owned;
+    bool has_small_att;  // some attractor has at most 10 states: the PBN family's reset loop terminates
 };
 
 template <class T>
@@ -225,6 +226,8 @@ extern "C" int pbn_env_create(const PbnNet *net, const PbnEnvDesc *d, PbnEnv **o
     v.force = d->force; v.dedup = d->dedup; v.control_write = d->control_write; v.n_control = d->n_control;
     v.successful_reward = d->successful_reward; v.wrong_attractor_cost = d->wrong_attractor_cost;
     v.n_att = d->n_att; v.tgt_first = d->tgt_first; v.n_tgt = d->n_tgt;
+    env->has_small_att = false;  // PBNEnv.reset redraws until it holds an attractor of at most 10 states (pbn_env.py:196-199)
+    for (int a = 0; a < d->n_att; a++) env->has_small_att |= d->att_off[a + 1] - d->att_off[a] <= 10;
     const int n_att_cubes = d->n_att > 0 ? d->att_off[d->n_att] : 0;
     v.n_cubes = n_att_cubes > d->tgt_first + d->n_tgt ? n_att_cubes : d->tgt_first + d->n_tgt;
     if (d->n_tgt == 0) v.n_cubes = n_att_cubes;
@@ -275,6 +278,13 @@ __device__ __forceinline__ void load_state(const Col &c, const u32 *g, long long
 }
 __device__ __forceinline__ void store_state(const Col &c, u32 *g, long long B, long long e, int w32) {
     for (int w = 0; w < w32; w++) g[(long long)w * B + e] = c.word(w);
+}
+
+// An intervention on node `pos`; an index outside the network (a policy network can emit anything) is ignored and counted —
+// it must not flip a bit of a neighbouring env's column or of the staged network image.
+__device__ __forceinline__ void flip_node(const Col &st, int pos, int n, int &bad) {
+    if (pos >= 0 && pos < n) st.flip((u32)pos);
+    else bad++;
 }
 
 // ---- shared-memory accesses by 32-bit shared-window address (the hot SSD loop keeps its base addresses in registers;
@@ -505,7 +515,7 @@ struct VecView {
     int enabled, autoreset;
     long long *ep_return;
     int *ep_len;
-    unsigned long long *stats;  // [6] episodes, return sum, length sum, successes, cap hits, env steps
+    unsigned long long *stats;  // [8] episodes, return sum, length sum, successes, cap hits, env steps, ignored interventions, -
     u32 *final_obs, *target_state;
     DrawView rdv;
 };
@@ -537,7 +547,7 @@ __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev,
 }
 __device__ __forceinline__ void vec_flush_stats(const VecView &vx, unsigned long long *s_stats) {
     __syncthreads();
-    if (vx.enabled && threadIdx.x < 6 && s_stats[threadIdx.x]) atomicAdd(&vx.stats[threadIdx.x], s_stats[threadIdx.x]);
+    if (vx.enabled && threadIdx.x < 8 && s_stats[threadIdx.x]) atomicAdd(&vx.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------- K1 sync, bit-sliced
@@ -671,10 +681,10 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
-    __shared__ unsigned long long s_stats[6];
+    __shared__ unsigned long long s_stats[8];
     stage(blob, nv.blob, nv.blob_bytes);
     stage(img, ev.img, ev.img_bytes);
-    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0;
+    if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,25 +696,25 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
     const int *act = actions + e * K;
-    int rew = 0, tm = 0, tr = 0, in = 0;
+    int rew = 0, tm = 0, tr = 0, in = 0, bad = 0;
     switch (ev.kind) {
     case PBN_ENV_PBN: {  // pbn_env.py:141-154, reward :171-183
         int a = act[0];
-        if (a != 0) st.flip(a);  // flips index `action` itself (Q3)
+        if (a != 0) flip_node(st, a, nv.n, bad);  // flips index `action` itself (Q3)
         micro_step<NET, MODE>(nv, blob, st, d); in = 1;
         if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew = 20; tm = 1; }
         else rew = -4 - (a != 0);
     } break;
     case PBN_ENV_PBCN: {  // pbcn_env.py:67-80
         int a = act[0];
-        if (a != 0) st.flip(a);
+        if (a != 0) flip_node(st, a, nv.n, bad);
         micro_step<NET, MODE>(nv, blob, st, d); in = 1;
         rew = pbcn_reward(ev, att_off, cubes, st, w32, tm);
     } break;
     case PBN_ENV_PBN_SD: {  // sampled_data.py:52-88
         int a = act[0], interval = act[1];
         for (int i = 0; i < interval; i++) {
-            if (a != 0) st.flip(a - 1);
+            if (a != 0) flip_node(st, a - 1, nv.n, bad);
             micro_step<NET, MODE>(nv, blob, st, d); in++;
             if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew += 20; tm = 1; }
             else { rew += -4 - (a != 0); tm = 0; }
@@ -735,7 +745,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     case PBN_ENV_PBCN_ST: {  // self_triggering.py:146-197: (prob 1..10, control bits...)
         const bool pbcn = ev.kind == PBN_ENV_PBCN_ST;
         const int a = pbcn ? 0 : act[0];
-        const double prob = (double)act[pbcn ? 0 : 1] / 10.0;  // convert value in [1,10] to [0.1 .. 1]
+        int pv = act[pbcn ? 0 : 1];                            // MultiDiscrete value 1..10 (self_triggering.py:29,120)
+        if (pv < 1 || pv > 10) { bad++; pv = pv < 1 ? 1 : 10; }  // a stop probability of 0 would never end the macro step
+        const double prob = (double)pv / 10.0;                 // convert value in [1,10] to [0.1 .. 1]
         const u32 stop_thr = (u32)ceil(prob * 2147483648.0);   // Philox: stop iff r31 < ceil(prob * 2^31)
         u32 cbits = 0;
         const u32 cmask = ev.n_control >= 32 ? 0xFFFFFFFFu : ((1u << ev.n_control) - 1u);
@@ -747,7 +759,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
         while (!end) {
             int r;
             if (!pbcn) {
-                if (a != 0) st.flip(a - 1);
+                if (a != 0) flip_node(st, a - 1, nv.n, bad);
                 micro_step<NET, MODE>(nv, blob, st, d);
                 if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { r = 20; tm = 1; }
                 else { r = -4 - (a != 0); tm = 0; }
@@ -779,6 +791,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     terminated[e] = (unsigned char)tm;
     truncated[e] = (unsigned char)tr;
     if (inner_steps) inner_steps[e] = in;
+    if (bad && vx.enabled) atomicAdd(&s_stats[6], 1ULL);  // env.steps whose intervention was out of range (ignored)
     d.done(dv, e);
     if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, nullptr, obs_state, B, e, env0, rew, tm, tr, in);
     }
@@ -803,26 +816,96 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 #define PBN_COOP_EXIT_AT 2  // group mode, queue not empty: stopped groups at which a call returns to finalize / refill
 #endif
 
+// is_attracting without early exits (the lockstep first pass: a warp's lanes test together, a branch per cube only diverges)
+__device__ __forceinline__ bool is_attracting_flat(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, int w32) {
+    if (ev.n_att == 0) return true;
+    const int n_cubes = att_off[ev.n_att];
+    bool hit = false;
+    if (w32 == 1) {
+        const u32 sw = st.word(0);
+        const uint2 *cv = reinterpret_cast<const uint2 *>(cubes);
+#pragma unroll 4
+        for (int c = 0; c < n_cubes; c++) hit |= (sw & cv[c].x) == cv[c].y;
+        return hit;
+    }
+    for (int c = 0; c < n_cubes; c++) {
+        const uint2 *cv = reinterpret_cast<const uint2 *>(cubes) + (size_t)c * w32;
+        bool ok = true;
+        for (int w = 0; w < w32; w++) ok &= (st.word(w) & cv[w].x) == cv[w].y;
+        hit |= ok;
+    }
+    return hit;
+}
+
+// ---- pieces of one env.step of the step-until-attractor envs, shared by the kernels below
+// the intervention: pbn_target.py:261-269 (one node) / pbn_target_multi.py:120-134 (a set of nodes, the observation captured
+// BEFORE the first update).  Returns the pending action cost (MULTI: -len(actions)).
+__device__ __forceinline__ int att_begin(const NetView &nv, const EnvView &ev, const Col &st, const Col &ob, const int *act, int K,
+                                         int &bad) {
+    const int w32 = nv.w32;
+    if (ev.kind != PBN_ENV_MULTI) {
+        const int a = act[0];
+        if (a != 0) flip_node(st, a - 1, nv.n, bad);
+        return 0;
+    }
+    int cnt = 0;
+    for (int k = 0; k < K; k++) {
+        const int a = act[k];
+        if (a < 0) continue;
+        if (ev.dedup) {
+            bool dup = false;
+            for (int j = 0; j < k; j++) dup |= (act[j] == a);
+            if (dup) continue;
+        }
+        cnt++;
+        if (a != 0) flip_node(st, a - 1, nv.n, bad);
+    }
+    for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
+    return -cnt;  // reward -= len(actions)
+}
+// reward and flags of a finished env.step; `ob` = the observation the loop ended on (MULTI), st = the state
+__device__ __forceinline__ void att_result(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, const Col &ob,
+                                           int w32, int ta, int pend, int &rew, int &tm) {
+    tm = 0;
+    if (ev.kind != PBN_ENV_MULTI) {  // PBNTargetEnv._get_reward, pbn_target.py:303-326: any cube of the target attractor
+        if (match_range(cubes, att_off[ta], att_off[ta + 1], st, w32)) { rew = 20; tm = 1; } else rew = -5;
+    } else {  // in_target returns at the first mismatch of the FIRST cube (Q12), pbn_target_multi.py:190-225
+        rew = pend;
+        if (att_off[ta] < att_off[ta + 1] && cube_match(cubes, att_off[ta], ob, w32)) { rew += 1000; tm = 1; }
+    }
+}
+
+// Budgeted / resumable execution (include/pbn_b200.h: PbnStepPlan).  Lists are {count, queue head, -, -, env ids...}.
+struct PlanView {
+    int budget, resume, dbg_a;
+    unsigned char *running;
+    int *list_in, *list_out;
+};
+
 template <int NET, int MODE, int TQ>
 __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
                                                             int *inner_steps, long long B, long long env0, long long per_block,
-                                                            int coop_on, int grp_mode, VecView vx) {
+                                                            int coop_on, int grp_mode, PlanView pl, VecView vx) {
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
     const int w32 = nv.w32;
     unsigned char *coop_buf = reinterpret_cast<unsigned char *>(sst + 2 * w32 * PBN_BLOCK);  // straggler-mode staging, per warp
     __shared__ int s_next;
-    __shared__ unsigned long long s_stats[6];
+    __shared__ unsigned long long s_stats[8];
     stage(blob, nv.blob, nv.blob_bytes);
     stage(img, ev.img, ev.img_bytes);
-    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0;
+    if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
     const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
-    const long long lo = (long long)blockIdx.x * per_block;
-    const long long hi = lo + per_block < B ? lo + per_block : B;
+    // work queue: a fresh step hands every block a contiguous range of envs, taken through a block-local counter; a resume
+    // pass takes the parked envs of the previous launch from one global queue, so the few long-running envs spread over the
+    // whole GPU whatever block first ran them
+    const bool resume = pl.resume != 0;
+    const long long lo = resume ? 0 : (long long)blockIdx.x * per_block;
+    const long long hi = resume ? (long long)pl.list_in[0] : (lo + per_block < B ? lo + per_block : B);
     // GROUP mode (predictor networks, Philox draws, real attractors): only every fourth lane owns an env — 64 per block at a
     // time — and every env is run from its second update on by a group of 4 .. 32 lanes (pbn_coop.cuh), 8 envs per warp side
     // by side: an update costs ~100 cycles there against ~2 500 for a lane running alone in the loop below, which then only
@@ -836,18 +919,57 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
     Col st{sst + threadIdx.x}, ob{sst + w32 * PBN_BLOCK + threadIdx.x};
     Draw<MODE> d;
     bool have = false;
-    long long e = 0, nxt = !grp ? lo + threadIdx.x : ((threadIdx.x & 3) == 0 ? lo + (threadIdx.x >> 2) : hi);
+    // a resume pass sizes its groups to the list: narrow groups carry more envs per instruction (an entry costs the warp the
+    // same ~16 ALU-pipe slots whether it serves 8 envs or one), wide ones finish an env sooner (130 against 50 cycles per
+    // update), and an SM whose 16 warps all run groups is bound by its ALU pipes, not by latency.  So a list that fits is
+    // dealt out STATICALLY (a racing queue hands the first blocks to arrive everything and leaves other SMs idle): over 4 of a
+    // block's 8 warps — one per scheduler — when that gives at most 8 envs per warp, else over all 8; what a longer list
+    // has left goes through the queue.
+    int quota = 8;
+    long long static_n = 0, per_slot = 0;  // list positions dealt out statically (resume passes), in rounds of per_slot
+    bool warp_on = true;
+    if (resume) {
+        const long long nb = gridDim.x;
+        int A = hi <= nb * 4 * 8 ? 4 : 8;
+        if (pl.dbg_a > 0) A = pl.dbg_a;
+        const long long q = (hi + nb * A - 1) / (nb * A);
+        quota = q < 1 ? 1 : (q > 8 ? 8 : (int)q);
+        per_slot = nb * A;
+        static_n = quota * per_slot;
+        warp_on = (int)(threadIdx.x >> 5) < A;
+    }
+    const bool owner_lane = !grp || ((threadIdx.x & 3) == 0 && (int)((threadIdx.x & 31) >> 2) < quota);
+    long long e = 0, nxt = hi;
+    if (owner_lane) {
+        if (!resume) nxt = lo + (grp ? threadIdx.x >> 2 : threadIdx.x);
+        else if (!grp) nxt = (long long)atomicAdd(&pl.list_in[1], 1);  // (lane mode: every lane pulls)
+        else if (warp_on)  // consecutive positions go to different blocks, i.e. SMs, first
+            nxt = (long long)((threadIdx.x & 31) >> 2) * per_slot + (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    }
+    if (resume && !grp) static_n = 0;
+    int used = 0;  // updates made for the current env in this launch (budget)
     int in = 0, pend = 0;
     for (;;) {
-        if (!have && nxt < hi) {
+        if (!have && nxt < hi && resume) {  // a parked env goes on from its saved state, update count and pending cost
+            e = pl.list_in[4 + nxt];
+            load_state(st, state, B, e, w32);
+            in = inner_steps[e];
+            pend = reward[e];
+            d.seek(dv, e, env0 + e, 2u * (u32)in, 0u);
+            if (multi)
+                for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
+            used = 0;
+            have = true;
+        } else if (!have && nxt < hi) {
             e = nxt;
             load_state(st, state, B, e, w32);
             d.init(dv, e, env0 + e);
             const int *act = actions + e * K;
             n_steps[e] += 1;
+            int bad = 0;
             if (!multi) {  // pbn_target.py:261-269
                 const int a = act[0];
-                if (a != 0) st.flip(a - 1);
+                if (a != 0) flip_node(st, a - 1, nv.n, bad);
             } else {  // pbn_target_multi.py:120-134
                 int cnt = 0;
                 for (int k = 0; k < K; k++) {
@@ -859,13 +981,15 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                         if (dup) continue;
                     }
                     cnt++;
-                    if (a != 0) st.flip(a - 1);
+                    if (a != 0) flip_node(st, a - 1, nv.n, bad);
                 }
                 pend = -cnt;  // reward -= len(actions)
                 for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));  // observation captured BEFORE the update (:133)
             }
+            if (bad && vx.enabled) atomicAdd(&s_stats[6], 1ULL);
             micro_step<NET, MODE, TQ>(nv, blob, st, d);
             in = 1;
+            used = 1;
             have = true;
         }
         // warp-uniform exit.  The full-mask vote is also where the lanes of the warp RE-CONVERGE every trip: without it,
@@ -876,11 +1000,20 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
             // while not force and not is_attracting_state(state): graph.step()                  (pbn_target.py:270-271)
             // while not is_attracting_state(observation): observation = graph.step()            (pbn_target_multi.py:135-146)
             const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting(ev, att_off, cubes, multi ? ob : st, w32);
-            if (!done) {
+            if (!done && pl.budget > 0 && used >= pl.budget) {  // out of budget: park the env for a resume pass
+                store_state(st, state, B, e, w32);
+                inner_steps[e] = in;
+                reward[e] = pend;
+                pl.running[e] = 1;
+                pl.list_out[4 + atomicAdd(&pl.list_out[0], 1)] = (int)e;
+                have = false;
+                nxt = resume ? static_n + (long long)atomicAdd(&pl.list_in[1], 1) : lo + atomicAdd(&s_next, 1);
+            } else if (!done) {
                 micro_step<NET, MODE, TQ>(nv, blob, st, d);
                 if (multi)
                     for (int w = 0; w < w32; w++) ob.set_word(w, st.word(w));
                 in++;
+                used++;
             } else {
                 int rew, tm = 0;
                 const int ta = target_att[e];
@@ -897,10 +1030,11 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                 const int tr = (n_steps[e] == ev.horizon);
                 truncated[e] = (unsigned char)tr;
                 if (inner_steps) inner_steps[e] = in;
+                if (pl.running) pl.running[e] = 0;
                 d.done(dv, e);
                 if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, const_cast<int *>(target_att), obs_state, B, e, env0, rew, tm, tr, in);
                 have = false;
-                nxt = lo + atomicAdd(&s_next, 1);
+                nxt = resume ? static_n + (long long)atomicAdd(&pl.list_in[1], 1) : lo + atomicAdd(&s_next, 1);
             }
         }
         if constexpr (MODE == PBN_DRAW_PHILOX && NET == PBN_NET_PRED) {
@@ -910,9 +1044,9 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
             const u32 lane = threadIdx.x & 31u;
             // the queue position is read by one lane and broadcast: the branch below runs full-mask collectives
             int qn = 0;
-            if (lane == 0u) qn = *reinterpret_cast<volatile int *>(&s_next);
+            if (lane == 0u) qn = resume ? *reinterpret_cast<volatile int *>(&pl.list_in[1]) : *reinterpret_cast<volatile int *>(&s_next);
             qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
-            const bool drained = lo + qn >= hi;
+            const bool drained = (resume ? static_n : lo) + qn >= hi;
             if (coop_on && hv != 0u && (grp || (__popc(live) <= PBN_COOP_MAX && drained))) {
                 const int nl = __popc(hv);
                 int k = 1;
@@ -923,18 +1057,23 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                 const int owner = active ? (int)__fns(hv, 0u, grp + 1) : 0;  // the grp-th live lane
                 const long long eL = __shfl_sync(0xFFFFFFFFu, e, owner);
                 const int inL = __shfl_sync(0xFFFFFFFFu, in, owner);
+                // the group stops at the cap or when the launch's budget for the env is used up, whichever comes first
+                int stop_in = ev.max_inner;
+                if (pl.budget > 0 && in - used + pl.budget < stop_in) stop_in = in - used + pl.budget;
+                stop_in = __shfl_sync(0xFFFFFFFFu, stop_in, owner);
                 u32 *colL = sst + (threadIdx.x & ~31u) + (u32)owner;
                 unsigned char *wb = coop_buf + (threadIdx.x >> 5) * coop_warp_bytes(w32);
                 // the call returns when `exit_at` groups have stopped: their owners finalize on the next trip (and, while the
                 // block's queue lasts, start the next env), the other envs come back here — in wider groups once the queue
                 // is empty, which is why the first stop ends the call then
                 const int exit_at = drained ? 1 : PBN_COOP_EXIT_AT;
-                const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g, 0u, wb, exit_at)
-                                         : coop_steps<TQ, false>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, active, g, 0u, wb, exit_at);
+                const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at)
+                                         : coop_steps<TQ, false>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at);
                 __syncwarp();
                 for (int r = 0; r < nl; r++) {          // hand each group's count back to the lane that owns the env
                     const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
                     if ((int)lane == (int)__fns(hv, 0u, r + 1) && v != in) {
+                        used += v - in;
                         in = v;
                         d.seek(dv, e, env0 + e, 2u * (u32)v, 0u);
                         if (multi)
@@ -944,6 +1083,82 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                 __syncwarp();
             }
         }
+    }
+    vec_flush_stats(vx, s_stats);
+}
+
+
+// First pass of a planned env.step (predictor networks, Philox draws): every thread owns one env, all envs start together and
+// make at most pl.budget updates, so the whole launch is in lockstep on the update index — the Philox block of the update
+// stream (one per two updates) is computed by all lanes at once, nobody pulls work, nothing diverges but the predicate "still
+// running".  Most envs reach an attractor within a few updates and are finished here (coalesced result stores after the loop);
+// the rest are parked for the resume pass (k_env_step_att, groups of lanes).  Same words, same result as any other split.
+template <int TQ>
+__global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+                                                              int *target_att, const int *actions, int K, u32 *obs_state,
+                                                              int *reward, unsigned char *terminated, unsigned char *truncated,
+                                                              int *inner_steps, long long B, long long env0, PlanView pl, VecView vx) {
+    unsigned char *blob = smem_raw;
+    unsigned char *img = smem_raw + nv.blob_bytes;
+    u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    const int w32 = nv.w32;
+    __shared__ unsigned long long s_stats[8];
+    stage(blob, nv.blob, nv.blob_bytes);
+    stage(img, ev.img, ev.img_bytes);
+    if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
+    const int *att_off = reinterpret_cast<const int *>(img);
+    const u32 *cubes = reinterpret_cast<const u32 *>(img + ev.off_cubes);
+    const long long e = (long long)blockIdx.x * PBN_BLOCK + threadIdx.x;
+    const bool valid = e < B;
+    const bool multi = ev.kind == PBN_ENV_MULTI;
+    Col st{sst + threadIdx.x}, ob{sst + w32 * PBN_BLOCK + threadIdx.x};
+    int pend = 0, bad = 0;
+    if (valid) {
+        load_state(st, state, B, e, w32);
+        n_steps[e] += 1;
+        pend = att_begin(nv, ev, st, ob, actions + e * K, K, bad);
+    }
+    __syncthreads();
+    Draw<PBN_DRAW_PHILOX> dummy;
+    const u32 c2 = (u32)(env0 + e), c3 = (u32)((u64)(env0 + e) >> 32);
+    u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    int in = 0;
+    bool run = valid;
+    for (int t = 0;; t++) {  // t updates made so far by every running env
+        if (t > 0 && run) {
+            // while not is_attracting_state(...): graph.step()  (pbn_target.py:270-271, pbn_target_multi.py:135-146; MULTI's
+            // first test looks at the observation captured before the first update)
+            const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting_flat(ev, att_off, cubes, (multi && in == 1) ? ob : st, w32);
+            run = !done;
+        }
+        if (t == pl.budget || !__any_sync(0xFFFFFFFFu, run)) break;
+        if ((t & 1) == 0) philox4x32_10_rk((u32)(t >> 1), dv.epoch, c2, c3, dv, x0, x1, x2, x3);
+        if (run) {
+            micro_step_words<PBN_NET_PRED, TQ>(nv, blob, st, (t & 1) ? x2 : x0, (t & 1) ? x3 : x1, dummy);
+            in++;
+        }
+    }
+    if (valid && run) {  // out of budget: park the env for a resume pass
+        store_state(st, state, B, e, w32);
+        inner_steps[e] = in;
+        reward[e] = pend;
+        pl.running[e] = 1;
+        pl.list_out[4 + atomicAdd(&pl.list_out[0], 1)] = (int)e;
+    } else if (valid) {
+        const Col &fo = (multi && in == 1) ? ob : st;  // MULTI: the observation is the state from the second update on
+        int rew, tm;
+        att_result(ev, att_off, cubes, st, fo, w32, target_att[e], pend, rew, tm);
+        store_state(st, state, B, e, w32);
+        if (obs_state) store_state(fo, obs_state, B, e, w32);
+        reward[e] = rew;
+        terminated[e] = (unsigned char)tm;
+        const int tr = (n_steps[e] == ev.horizon);
+        truncated[e] = (unsigned char)tr;
+        inner_steps[e] = in;
+        pl.running[e] = 0;
+        if (dv.used) { dv.used[2 * e] = 2 * in; dv.used[2 * e + 1] = 0; }
+        if (bad && vx.enabled) atomicAdd(&s_stats[6], 1ULL);
+        if (vx.enabled) vec_finish<PBN_DRAW_PHILOX>(nv, ev, vx, s_stats, state, n_steps, target_att, obs_state, B, e, env0, rew, tm, tr, in);
     }
     vec_flush_stats(vx, s_stats);
 }
@@ -1254,8 +1469,8 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
                             const u32 baseL = __shfl_sync(0xFFFFFFFFu, pos - (u32)in, owner);
                             u32 *colL = a.sst + (threadIdx.x & ~31u) + (u32)owner;
                             unsigned char *wb = a.coop_buf + (threadIdx.x >> 5) * coop_warp_bytes(w32);
-                            const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL, wb, 32)
-                                                     : coop_steps<TQ, false>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, on, g, baseL, wb, 32);
+                            const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, a.ev.max_inner, on, g, baseL, wb, 32)
+                                                     : coop_steps<TQ, false>(nv, a.ev, a.dv, a.blob, a.att_off, a.cubes, colL, idL, inL, a.ev.max_inner, on, g, baseL, wb, 32);
                             __syncwarp();
                             for (int r = 0; r < nl; r++) {
                                 const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
@@ -1523,7 +1738,7 @@ extern "C" int pbn_rollout(const PbnNet *net, uint32_t *state, int64_t B, int64_
 static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const int32_t *target_att,
                          const int32_t *actions, int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated,
                          uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
-                         const PbnVecState *vec, void *stream, double *reward_f64 = nullptr) {
+                         const PbnVecState *vec, void *stream, double *reward_f64 = nullptr, const PbnStepPlan *plan = nullptr) {
     if (!env || !state || !actions || !reward || !terminated || !truncated || B < 0 || K < 1) return fail(PBN_ERR_ARG, "bad argument");
     {
         const int kd = env->v.kind;
@@ -1549,6 +1764,7 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
             if (int rc = check_draws(&vec->reset_draws)) return rc;
             const bool tgt = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
             if (ev.n_att < (ev.kind == PBN_ENV_TARGET ? 2 : 1)) return fail(PBN_ERR_ARG, "autoreset needs attractors");
+            if (!tgt && !env->has_small_att) return fail(PBN_ERR_ARG, "autoreset needs an attractor with at most 10 states (pbn_env.py:196-199)");
             if (tgt && !vec->target_state) return fail(PBN_ERR_ARG, "autoreset of target envs needs target_state");
             vx.rdv = make_draws(&vec->reset_draws);
         }
@@ -1559,12 +1775,39 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
     const int block = block_for(B);
     const unsigned grid = (unsigned)((B + block - 1) / block);
     const bool att = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
+    cudaStream_t s = (cudaStream_t)stream;
+    PlanView pl;
+    memset(&pl, 0, sizeof pl);
+    if (plan) {
+        if (!att) return fail(PBN_ERR_UNSUPPORTED, "a step plan applies to the step-until-attractor envs (TARGET, MULTI)");
+        if (dv.mode != PBN_DRAW_PHILOX) return fail(PBN_ERR_UNSUPPORTED, "a step plan needs Philox draws (a resumed env re-enters its stream by position)");
+        if (!plan->running || !plan->work || !inner_steps) return fail(PBN_ERR_ARG, "a step plan needs running, work and inner_steps");
+        if (plan->budget < 0 || (plan->phase != 0 && plan->phase != 1)) return fail(PBN_ERR_ARG, "bad step plan");
+        if (ev.kind == PBN_ENV_MULTI && plan->budget == 1) return fail(PBN_ERR_ARG, "MULTI envs need a budget of at least 2 updates");
+        pl.budget = plan->budget; pl.resume = plan->resume != 0;
+        if (const char *dbg = getenv("PBN_PLAN_A")) pl.dbg_a = atoi(dbg);  // experiments: active warps per block of a resume pass
+        pl.running = plan->running;
+        pl.list_out = plan->work + (size_t)plan->phase * (size_t)(B + 4);
+        pl.list_in = plan->work + (size_t)(plan->phase ^ 1) * (size_t)(B + 4);
+        CK(cudaMemsetAsync(pl.list_out, 0, 16, s));
+    }
     // two columns per env + (step-until-attractor kernel) the per-warp staging of its straggler mode
     size_t smem = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)2 * nv.w32 * block * 4;
     const size_t coop_bytes = (size_t)(block / 32) * coop_warp_bytes(nv.w32);
-    const int coop_on = att && smem + coop_bytes <= 200 * 1024;  // images that leave no room run without the straggler mode
+    // a budgeted first pass has no tail to cut (every lane owns an env, nobody runs past the budget); images that leave no
+    // room run without the group machinery as well
+    const int coop_on = att && smem + coop_bytes <= 200 * 1024 && !(plan && !pl.resume && pl.budget > 0);
     if (coop_on) smem += coop_bytes;
-    cudaStream_t s = (cudaStream_t)stream;
+    if (plan && !pl.resume && pl.budget > 0 && nv.kind == PBN_NET_PRED) {  // lockstep first pass (Philox: checked above)
+#define FIRST(TQ)                                                                                                 \
+        if (int rc = set_smem(k_env_step_first<TQ>, smem)) return rc;                                             \
+        k_env_step_first<TQ><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, const_cast<int32_t *>(target_att), actions, K, \
+                                                      obs_state, reward, terminated, truncated, inner_steps, B, env0, pl, vx)
+        if (nv.ts == 4) { FIRST(1); } else if (nv.ts == 16) { FIRST(4); } else { FIRST(0); }
+#undef FIRST
+        CK(cudaGetLastError());
+        return PBN_OK;
+    }
 #define CALL(NK, MD, TQ)                                                                                          \
     if (att) {                                                                                                    \
         if (int rc = set_smem(k_env_step_att<NK, MD, TQ>, smem)) return rc;                                       \
@@ -1576,11 +1819,11 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
         const int grp_mode = coop_on && NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && ev.n_att > 0 && !ev.force; \
         const long long cap_grid = grp_mode ? (B + PBN_BLOCK / 4 - 1) / (PBN_BLOCK / 4) : (long long)grid;        \
-        if (pgrid > cap_grid) pgrid = cap_grid;                                                                   \
+        if (pgrid > cap_grid) pgrid = cap_grid;  /* (a resume pass learns its env count on the device) */         \
         const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
         pgrid = (B + per_block - 1) / per_block;                                                                  \
         k_env_step_att<NK, MD, TQ><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, coop_on, grp_mode, vx); \
+                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, coop_on, grp_mode, pl, vx); \
     } else {                                                                                                      \
         const size_t smem1 = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)nv.w32 * block * 4; /* one column per env */ \
         if (int rc = set_smem(k_env_step<NK, MD>, smem1)) return rc;                                              \
@@ -1619,6 +1862,15 @@ extern "C" int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps
                          env0, draws, vec, stream);
 }
 
+extern "C" int pbn_env_step_plan(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
+                                 int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
+                                 int32_t *inner_steps, const PbnVecState *vec, const PbnStepPlan *plan, int64_t B, int64_t env0,
+                                 const PbnDraws *draws, void *stream) {
+    if (!plan) return fail(PBN_ERR_ARG, "plan is null");
+    return env_step_impl(env, state, n_steps, target_att, actions, K, obs_state, reward, terminated, truncated, inner_steps, B,
+                         env0, draws, vec, stream, nullptr, plan);
+}
+
 extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
                              const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream) {
     if (!env || !state || B < 0) return fail(PBN_ERR_ARG, "bad argument");
@@ -1626,7 +1878,12 @@ extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_step
     if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
         if (!n_steps || !target_att) return fail(PBN_ERR_ARG, "target envs need n_steps and target_att");
         if (ev.n_att < (ev.kind == PBN_ENV_TARGET ? 2 : 1)) return fail(PBN_ERR_ARG, "reset needs attractors (sample of 2, pbn_target.py:333)");
-    } else if (ev.n_att < 1) return fail(PBN_ERR_ARG, "reset needs attractors");
+    } else {
+        if (ev.n_att < 1) return fail(PBN_ERR_ARG, "reset needs attractors");
+        // pbn_env.py:196-199 redraws an attractor until one has at most 10 states; in Python that loop can be interrupted, on
+        // the device it would hang the GPU
+        if (!env->has_small_att) return fail(PBN_ERR_ARG, "reset needs an attractor with at most 10 states (pbn_env.py:196-199 would loop forever)");
+    }
     if (int rc = check_draws(draws)) return rc;
     if (B == 0) return PBN_OK;
     const DrawView dv = make_draws(draws);
@@ -1737,6 +1994,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     memset(sp.tgt, 0, sizeof sp.tgt);
     for (int k = 0; k < g; k++) {
         if (tgt[k] < 0 || tgt[k] >= nv.n) return fail(PBN_ERR_ARG, "target node out of range");
+        if (tgt[k] > 32767) return fail(PBN_ERR_UNSUPPORTED, "target node indices above 32767 are not supported");
         sp.tgt[k] = (short)tgt[k];
     }
     // fast bucket path: targets are consecutive ascending nodes inside one 32-bit state word

@@ -23,8 +23,11 @@
 #define PBN_COOP_NB 2            // Philox blocks per lane and batch (two chains in flight: the latency of one)
 #define PBN_COOP_ENTRIES (32 * 2 * PBN_COOP_NB)  // per warp: two per Philox block
 #define PBN_COOP_ENTRY_BYTES 32  // {g0, g1, g2, g3} {Lrot, mask, word address, cube word offset}
-// per-warp staging bytes: the entries + one checkpoint column (w32 words) for each of up to 8 groups
-__host__ __device__ inline int coop_warp_bytes(int w32) { return PBN_COOP_ENTRIES * PBN_COOP_ENTRY_BYTES + ((8 * w32 * 4 + 15) & ~15); }
+// per-warp staging bytes: the entries (+ 16 bytes of padding per group: the groups of a warp read the same entry index at the
+// same time, and regions a multiple of 128 bytes apart would put all those 16-byte reads on the same four banks) + one
+// checkpoint column (w32 words) for each of up to 8 groups
+#define PBN_COOP_ENT_BYTES (PBN_COOP_ENTRIES * PBN_COOP_ENTRY_BYTES + 8 * 16)
+__host__ __device__ inline int coop_warp_bytes(int w32) { return PBN_COOP_ENT_BYTES + ((8 * w32 * 4 + 15) & ~15); }
 
 __device__ __forceinline__ uint4 lds_v4(u32 a) {
     uint4 v;
@@ -113,27 +116,30 @@ struct CoopCube {
 };
 
 // One batch entry after the other: test the state BEFORE the entry (off the dependent chain), then apply it.  Every lane
-// tests two cubes (sub and sub + g); EXTRA: more than 2g cubes, the surplus is tested directly.  Returns the first entry
-// whose before-state matched.
-template <bool W1, bool EXTRA>
+// tests its cube `sub` (TWO: and cube sub + g; EXTRA: more than 2g cubes, the surplus is tested directly).  Returns the first
+// entry whose before-state matched.  The next entry is fetched one trip ahead at a constant offset — past the last entry that
+// reads the neighbouring group's first entry or the checkpoint area, never used.
+template <bool W1, bool TWO, bool EXTRA>
 __device__ __forceinline__ int coop_phase_b(u32 ebuf, int E, u32 &st, u32 col, u32 care0, u32 val0, u32 care1, u32 val1, CoopCube &cc,
                                             const u32 *cubes, int n_cubes, int w32, int g, u32 sub) {
     int first = E;
     uint4 ea = lds_v4(ebuf), eb = lds_v4(ebuf + 16u);
     for (int e0 = 0; e0 < E; e0 += 4) {
+        const u32 eb0 = ebuf + (u32)e0 * PBN_COOP_ENTRY_BYTES;
+        u32 m4 = 0u;  // bit k: the state before entry e0 + k matched
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int e = e0 + k;
-            const u32 nx = ebuf + (u32)((e + 1) & (E - 1)) * PBN_COOP_ENTRY_BYTES;
-            const uint4 na = lds_v4(nx), nb = lds_v4(nx + 16u);  // one trip ahead: these loads never wait on the state
+            const uint4 na = lds_v4(eb0 + (k + 1) * PBN_COOP_ENTRY_BYTES), nb = lds_v4(eb0 + (k + 1) * PBN_COOP_ENTRY_BYTES + 16u);
             if constexpr (W1) {
-                bool hit = ((st & care0) == val0) | ((st & care1) == val1);
+                bool hit = (st & care0) == val0;
+                if constexpr (TWO) hit |= (st & care1) == val1;
                 if constexpr (EXTRA)
                     for (int c = (int)sub + 2 * g; c < n_cubes; c += g) hit |= (st & cubes[2 * c]) == cubes[2 * c + 1];
-                first = (hit && e < first) ? e : first;
+                if (hit) m4 |= 1u << k;
                 st = coop_merge(rotr32(st, ea.x), rotr32(st, ea.y), rotr32(st, ea.z), rotr32(st, ea.w), eb.x, eb.y, st);
             } else {
-                bool hit = (cc.mm == 0) | (cc.mm1 == 0);
+                bool hit = cc.mm == 0;
+                if constexpr (TWO) hit |= cc.mm1 == 0;
                 if constexpr (EXTRA)
                     for (int c = (int)sub + 2 * g; c < n_cubes; c += g) {
                         const u32 *pc = cubes + (size_t)c * w32 * 2;
@@ -141,39 +147,45 @@ __device__ __forceinline__ int coop_phase_b(u32 ebuf, int E, u32 &st, u32 col, u
                         for (int w = 0; w < w32; w++) ok &= (lds_u32(col + 1024u * w) & pc[2 * w]) == pc[2 * w + 1];
                         hit |= ok;
                     }
-                first = (hit && e < first) ? e : first;
-                const uint2 cw = lds_v2(cc.addr + eb.w), cv = lds_v2(cc.addr1 + eb.w);  // (care, value) of the word the entry writes
+                if (hit) m4 |= 1u << k;
+                const uint2 cw = lds_v2(cc.addr + eb.w);  // (care, value) of the word the entry writes
                 const u32 w0 = lds_u32(ea.x >> 8), w1 = lds_u32(ea.y >> 8), w2 = lds_u32(ea.z >> 8), w3 = lds_u32(ea.w >> 8);
                 const u32 old = lds_u32(eb.z);
                 const u32 nw = coop_merge(rotr32(w0, ea.x), rotr32(w1, ea.y), rotr32(w2, ea.z), rotr32(w3, ea.w), eb.x, eb.y, old);
                 sts_u32(eb.z, nw);
                 const u32 flip = old ^ nw;                     // the written bit, if it changed
                 cc.mm += (flip & cw.x) ? (((nw ^ cw.y) & eb.y) ? 1 : -1) : 0;  // the cube cares: one mismatch more or one fewer
-                cc.mm1 += (flip & cv.x) ? (((nw ^ cv.y) & eb.y) ? 1 : -1) : 0;
+                if constexpr (TWO) {
+                    const uint2 cv = lds_v2(cc.addr1 + eb.w);
+                    cc.mm1 += (flip & cv.x) ? (((nw ^ cv.y) & eb.y) ? 1 : -1) : 0;
+                }
             }
             ea = na; eb = nb;
         }
+        if (m4 != 0u && first == E) first = e0 + __ffs((int)m4) - 1;
     }
     return first;
 }
 
 // Runs the loop for 32/g envs at once, group r (lanes r*g .. r*g+g-1) on the env whose column is col_ptr (group-uniform,
-// like env_id, in, pos_base and active).  pos_base = updates the env's stream had served before this env.step began: update
-// number `in` of the step takes words 2*(pos_base + in), +1.  Returns the group's update count.  The call returns when
+// like env_id, in, stop_in, pos_base and active).  pos_base = updates the env's stream had served before this env.step
+// began: update number `in` of the step takes words 2*(pos_base + in), +1.  A group stops at the first attracting state or
+// when its count reaches stop_in (the inner-step cap, or less under a budget).  Returns the group's update count.  The call returns when
 // `exit_at` groups have stopped since it began (1: at the first, so the caller can re-form wider groups) or none is left.
 // wbuf: coop_warp_bytes(w32) bytes of shared memory owned by this warp, 16-byte aligned.
 template <int TQ, bool W1>
 __device__ __forceinline__ int coop_steps(const NetView &nv, const EnvView &ev, const DrawView &dv, const unsigned char *blob,
                                           const int *att_off, const u32 *cubes, u32 *col_ptr, long long env_id, int in,
-                                          bool active, int g, u32 pos_base, unsigned char *wbuf, int exit_at) {
+                                          int stop_in, bool active, int g, u32 pos_base, unsigned char *wbuf, int exit_at) {
     const u32 lane = threadIdx.x & 31u;
     const u32 sub = lane & (u32)(g - 1), gbase = lane & ~(u32)(g - 1);
     const u32 gmask = (g == 32 ? 0xFFFFFFFFu : ((1u << g) - 1u)) << gbase;
     const int w32 = nv.w32;
     const int E = 2 * PBN_COOP_NB * g;
     const u32 lane_ent = (2u * PBN_COOP_NB) * PBN_COOP_ENTRY_BYTES;  // bytes of entries per lane
-    const u32 ebuf = smem_addr(wbuf) + gbase * lane_ent;
-    const u32 ckp = smem_addr(wbuf) + PBN_COOP_ENTRIES * PBN_COOP_ENTRY_BYTES + (gbase >> (__ffs(g) - 1)) * (u32)w32 * 4u;
+    const u32 grp_idx = gbase >> (__ffs(g) - 1);
+    const u32 ebuf = smem_addr(wbuf) + gbase * lane_ent + grp_idx * 16u;
+    const u32 ckp = smem_addr(wbuf) + PBN_COOP_ENT_BYTES + grp_idx * (u32)w32 * 4u;
     const u32 col = smem_addr(col_ptr);
     const int n_cubes = att_off[ev.n_att];
     const bool has_cube = (int)sub < n_cubes, has_cube1 = (int)sub + g < n_cubes;
@@ -237,13 +249,14 @@ __device__ __forceinline__ int coop_steps(const NetView &nv, const EnvView &ev, 
 #endif
         // ---- phase B
         int first;
-        if (n_cubes <= 2 * g) first = coop_phase_b<W1, false>(ebuf, E, st, col, care0, val0, care1, val1, cc, cubes, n_cubes, w32, g, sub);
-        else first = coop_phase_b<W1, true>(ebuf, E, st, col, care0, val0, care1, val1, cc, cubes, n_cubes, w32, g, sub);
+        if (n_cubes <= g) first = coop_phase_b<W1, false, false>(ebuf, E, st, col, care0, val0, care1, val1, cc, cubes, n_cubes, w32, g, sub);
+        else if (n_cubes <= 2 * g) first = coop_phase_b<W1, true, false>(ebuf, E, st, col, care0, val0, care1, val1, cc, cubes, n_cubes, w32, g, sub);
+        else first = coop_phase_b<W1, true, true>(ebuf, E, st, col, care0, val0, care1, val1, cc, cubes, n_cubes, w32, g, sub);
 #ifdef PBN_COOP_PROF
         const long long t2 = clock64();
 #endif
         // ---- stop entry: first match of any lane's cubes, or the entry at which the cap is reached
-        int cap = ev.max_inner - in;
+        int cap = stop_in - in;
         cap = (cap < 0 ? 0 : cap) + (int)u0;
         first = first < cap ? first : cap;
         if (g == 32) first = __reduce_min_sync(0xFFFFFFFFu, first);

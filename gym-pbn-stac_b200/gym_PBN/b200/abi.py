@@ -47,6 +47,10 @@ class PbnVecState(C.Structure):
                 ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws)]
 
 
+class PbnStepPlan(C.Structure):
+    _fields_ = [("running", C.c_void_p), ("work", C.c_void_p), ("budget", C.c_int32), ("resume", C.c_int32), ("phase", C.c_int32)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "pbn_net_create": (C.c_int, [C.POINTER(PbnNetDesc), C.POINTER(C.c_void_p)]),
@@ -65,6 +69,9 @@ EXPORTS = {
     "pbn_vec_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PbnVecState), C.c_int64, C.c_int64,
                                C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_env_step_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PbnVecState), C.POINTER(PbnStepPlan),
+                                    C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_rand_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),

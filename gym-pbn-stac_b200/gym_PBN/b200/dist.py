@@ -34,9 +34,10 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
 
 
 class EpisodeStats:
-    """Running episode statistics of a VectorEnv: [episodes, return sum, length sum, successes, cap hits, env steps]."""
+    """Running episode statistics of a VectorEnv: [episodes, return sum, length sum, successes, cap hits, env steps, env steps
+    whose action was out of range (the intervention is ignored on the device and counted here), reserved]."""
 
-    FIELDS = ("episodes", "return_sum", "length_sum", "successes", "cap_hits", "env_steps")
+    FIELDS = ("episodes", "return_sum", "length_sum", "successes", "cap_hits", "env_steps", "invalid_actions", "reserved")
 
     def __init__(self, device):
         self.v = torch.zeros(len(self.FIELDS), dtype=torch.int64, device=device)

@@ -27,6 +27,26 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class on_device:
+    """`with on_device(dev):` — make dev current for the block and put the caller's device back afterwards; costs two integer
+    compares when dev already is current (the hot paths call this per launch)."""
+
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, device):
+        self.dev = device.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def require_cuda(device):
     device = torch.device(device if device is not None else "cuda")
     if device.type != "cuda" or not torch.cuda.is_available():
@@ -69,6 +89,8 @@ class EnvImage:
                  gamma=None, max_interval=None):
         self.net, self.kind = net, kind
         self.n_att = len(attractors)
+        self.force = bool(force)
+        self.max_inner = int(max_inner)
         cube, off, tgt_first, n_tgt = compile_cubes(net.n, attractors, targets)
         self._keep = (cube, off)
         d = abi.PbnEnvDesc(kind=kind, horizon=int(horizon), max_inner=int(max_inner), force=int(bool(force)),
@@ -138,6 +160,16 @@ class Simulator:
         self.launches = 0
         self._vec_cache = None
         self._unpack_out = None
+        # step plan of the step-until-attractor envs (include/pbn_b200.h: PbnStepPlan): a full env.step is a first pass with
+        # plan_budgets[0] updates per env (every lane owns an env; most envs finish there), resume passes with the further
+        # budgets (the envs still outside every attractor, run by groups of lanes and spread over the whole GPU: each pass
+        # sheds the envs that finish, so the next one runs fewer envs per warp in wider, faster groups) and a last pass to the
+        # end; () = one launch does everything
+        self.plan_budgets = (32, 256)
+        self.running = None   # bool [B]: envs whose env.step is unfinished (budgeted stepping)
+        self._work = None     # int32 [2 * (B + 4)]: the two parking lists
+        self._plan_phase = 0
+        self._plan_draws = None
 
     # ---- draws
     def reseed(self, seed):
@@ -164,9 +196,8 @@ class Simulator:
         planes = self.state if planes is None else planes
         if out is None:
             out = torch.empty((self.B, self.net.n), dtype=torch.uint8, device=self.device)
-        if torch.cuda.current_device() != self.device.index:
-            torch.cuda.set_device(self.device)
-        abi.check(abi.lib().pbn_unpack_state(_ptr(planes), self.B, self.net.n, _ptr(out), _stream()))
+        with on_device(self.device):
+            abi.check(abi.lib().pbn_unpack_state(_ptr(planes), self.B, self.net.n, _ptr(out), _stream()))
         self.launches += 1
         return out
 
@@ -187,11 +218,55 @@ class Simulator:
                                             C.byref(d), _stream()))
             self.launches += 1
 
-    def env_step(self, env: EnvImage, actions, replay=None):
+    def _plan_buffers(self):
+        if self.running is None:
+            self.running = torch.zeros(self.B, dtype=torch.bool, device=self.device)
+            self._work = torch.zeros(2 * (self.B + 4), dtype=torch.int32, device=self.device)
+
+    def _plan_call(self, env, actions, d, budget, resume, vec=None):
+        self._plan_buffers()
+        plan = abi.PbnStepPlan(running=_ptr(self.running), work=_ptr(self._work), budget=int(budget), resume=int(resume),
+                               phase=self._plan_phase)
+        self._plan_phase ^= 1  # the next call reads the list this one wrote
+        with torch.cuda.device(self.device):
+            abi.check(abi.lib().pbn_env_step_plan(
+                env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att), _ptr(actions), actions.shape[1],
+                _ptr(self.obs_state), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner),
+                C.byref(vec) if vec is not None else None, C.byref(plan), self.B, self.env0, C.byref(d), _stream()))
+            self.launches += 1
+
+    def _plannable(self, env, replay):
+        return (replay is None and env.kind in (abi.ENV_TARGET, abi.ENV_MULTI) and env.n_att > 0 and not env.force
+                and len(self._passes(env)) > 1)
+
+    def _passes(self, env):
+        """Budgets of the passes of one full env.step: plan_budgets as far as the cap can exceed them, then 0 (to the end)."""
+        out, spent = [], 0
+        for b in self.plan_budgets:
+            b = max(int(b), 2)
+            if spent + b >= env.max_inner:
+                break
+            out.append(b)
+            spent += b
+        return out + [0]
+
+    def env_step(self, env: EnvImage, actions, replay=None, budget=None):
         """actions: int32 device tensor [B] or [B][K].  Results land in self.reward / terminated / truncated / inner /
-        obs_state (overwritten by the next call)."""
+        obs_state (overwritten by the next call).
+
+        budget (step-until-attractor envs, Philox draws): at most that many updates per env in this launch; envs still
+        outside every attractor are parked (self.running) and go on with env_step_resume — any split gives the result of
+        the unsplit step, bit for bit.  budget=None runs the step to its end."""
         actions = actions.to(self.device, dtype=torch.int32).reshape(self.B, -1).contiguous()
         d = self._draws(replay)
+        if budget is not None or self._plannable(env, replay):
+            self._plan_draws, self._plan_actions = d, actions
+            if budget is not None:
+                self._plan_call(env, actions, d, budget, 0)
+            else:
+                for k, b in enumerate(self._passes(env)):
+                    self._plan_call(env, actions, d, b, int(k > 0))
+            return
         if env.kind in (abi.ENV_PBN_ST, abi.ENV_PBCN_ST):  # discounted float64 reward (self.reward_f64), interval in self.inner
             if getattr(self, "reward_f64", None) is None:
                 self.reward_f64 = torch.zeros(self.B, dtype=torch.float64, device=self.device)
@@ -209,13 +284,20 @@ class Simulator:
                                              self.env0, C.byref(d), _stream()))
             self.launches += 1
 
+    def env_step_resume(self, env: EnvImage, budget=0):
+        """Continues the envs a budgeted env_step (or env_step_resume) left running; budget=0 runs them to the end."""
+        if self._plan_draws is None:
+            raise abi.PbnError("env_step_resume without a budgeted env_step")
+        self._plan_call(env, self._plan_actions, self._plan_draws, budget, 1)
+
     def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True):
         """Fused vector-env step (one launch): env.step for every env + episode bookkeeping + statistics + reset of the envs
         that finished.  Consumes two epochs (step, reset) exactly like env_step followed by a masked env_reset."""
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, dtype=torch.int32).contiguous()
         K = actions.numel() // self.B
-        key = (env.handle.value, ep_return.data_ptr(), final_obs.data_ptr() if final_obs is not None else 0, bool(autoreset))
+        key = (env.handle.value, ep_return.data_ptr(), final_obs.data_ptr() if final_obs is not None else 0, bool(autoreset),
+               tuple(self.plan_budgets))
         c = self._vec_cache
         if c is None or c["key"] != key:  # the buffers never move: build the argument block once
             d, rd = abi.PbnDraws(mode=abi.DRAW_PHILOX), abi.PbnDraws(mode=abi.DRAW_PHILOX)
@@ -224,19 +306,31 @@ class Simulator:
             head = (env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att))
             tail = (_ptr(self.obs_state), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner))
             c = self._vec_cache = {"key": key, "d": d, "v": v, "head": head, "tail": tail, "fn": abi.lib().pbn_vec_step}
+            if self._plannable(env, None):  # budgeted start, resume passes (see env_step)
+                self._plan_buffers()
+                c["plans"] = [abi.PbnStepPlan(running=_ptr(self.running), work=_ptr(self._work), budget=b, resume=int(k > 0), phase=k & 1)
+                              for k, b in enumerate(self._passes(env))]
+                c["fn2"] = abi.lib().pbn_env_step_plan
         d, v = c["d"], c["v"]
         d.seed = v.reset_draws.seed = self.seed
         d.epoch = self.epoch & 0xFFFFFFFF
         v.reset_draws.mode = abi.DRAW_PHILOX
         v.reset_draws.epoch = (self.epoch + 1) & 0xFFFFFFFF
         self.epoch += 2
-        if torch.cuda.current_device() != self.device.index:
-            torch.cuda.set_device(self.device)
-        rc = c["fn"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(v), self.B, self.env0, C.byref(d),
-                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        if rc:
-            abi.check(rc)
-        self.launches += 1
+        with on_device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if "plans" in c:
+                for plan in c["plans"]:
+                    rc = c["fn2"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(v), C.byref(plan), self.B,
+                                  self.env0, C.byref(d), stream)
+                    if rc:
+                        abi.check(rc)
+                    self.launches += 1
+                return
+            rc = c["fn"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(v), self.B, self.env0, C.byref(d), stream)
+            if rc:
+                abi.check(rc)
+            self.launches += 1
 
     def env_reset(self, env: EnvImage, mask=None, replay=None):
         if mask is not None:

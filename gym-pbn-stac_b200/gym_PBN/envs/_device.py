@@ -45,8 +45,9 @@ class DeviceEnvMixin:
 
     def _single_io(self, K):
         """Pinned host staging for the single env: actions up, {reward, flags, inner, state, obs} down in ONE read-back."""
-        io = getattr(self, "_io", None)
-        if io is None or io["K"] != K:
+        ios = self.__dict__.setdefault("_ios", {})  # one staging block per action width: built once each, never rebuilt
+        io = ios.get(K)
+        if io is None:
             sim, w32 = self.sim, self.network.w32
             host = torch.empty(12 + 8 * w32, dtype=torch.uint8).pin_memory()
             acts_host = torch.empty(K, dtype=torch.int32).pin_memory()
@@ -60,7 +61,7 @@ class DeviceEnvMixin:
             io["fetch_args"] = (p(sim.reward), p(sim.terminated), p(sim.truncated), p(sim.inner), p(sim.state),
                                 p(sim.obs_state), w32, 1, 0, p(io["scratch"]), p(host))
             io["up_args"] = (p(io["acts_dev"]), p(acts_host), 4 * K)
-            self._io = io
+            ios[K] = io
         return io
 
     def _run_step(self, image, actions):
@@ -70,15 +71,14 @@ class DeviceEnvMixin:
         io = self._single_io(len(acts))
         io["acts_np"][:] = acts
         sim, lib = self.sim, abi.lib()
-        if torch.cuda.current_device() != sim.device.index:
-            torch.cuda.set_device(sim.device)
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         queue = getattr(self, "_replays", None)
         replay = queue.pop(0) if queue else None
         d = sim._draws(replay)
-        abi.check(lib.pbn_upload(*io["up_args"], stream))
-        abi.check(lib.pbn_env_step(*io["step_args"](image, d, stream)))
-        abi.check(lib.pbn_fetch_step_host(*io["fetch_args"], stream))
+        with engine.on_device(sim.device):  # the caller's current device is restored (a process may hold several GPUs)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            abi.check(lib.pbn_upload(*io["up_args"], stream))
+            abi.check(lib.pbn_env_step(*io["step_args"](image, d, stream)))
+            abi.check(lib.pbn_fetch_step_host(*io["fetch_args"], stream))
         sim.launches += 2
         buf, n, w4 = io["np"], self.network.n, 4 * self.network.w32
         head = buf[:12].view(np.int32)

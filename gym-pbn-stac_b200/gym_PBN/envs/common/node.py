@@ -24,11 +24,11 @@ class Node:
         return float(self.function.reshape(-1)[idx])
 
     def compute_next_value(self, state):
-        """Host-side stochastic evaluation with one draw from Python's `random` (common/node.py:34-38); the device step does
-        the same comparison with Philox or replayed draws."""
-        import random
-
-        return random.uniform(0, 1) < self.get_next_value_prob(state)
+        """Host-side stochastic evaluation with one draw from NumPy's legacy global generator — the reference's module does
+        `from numpy import random`, so its `random.uniform(0, 1)` is numpy.random.uniform (common/node.py:2,34-38) and a seeded
+        host replay consumes the same stream here.  The device step does the same comparison with Philox or replayed draws."""
+        u = np.random.uniform(0, 1)
+        return u < self.get_next_value_prob(state)
 
     def __str__(self):
         return f"{self.name}{' (Control)' if self.is_control else ''}"

@@ -145,6 +145,23 @@ def eval_increase(env, model, original_ssd=None, iters=1_200_000, resets=300, bi
     return float(delta.loc[states, "Value"].sum())
 
 
+def _step_limit(env):
+    """max_episode_steps of an env made through the registry: the spec's value, else the TimeLimit wrapper's own counter
+    (gymnasium keeps it in `_max_episode_steps`, which Wrapper.__getattr__ hides, so the wrappers are walked; the in-repo
+    stand-in calls it `_max`)."""
+    e = env
+    while e is not None:
+        spec = e.__dict__.get("spec") if hasattr(e, "__dict__") else None
+        if spec is not None and getattr(spec, "max_episode_steps", None):
+            return int(spec.max_episode_steps)
+        for name in ("_max_episode_steps", "_max"):
+            v = e.__dict__.get(name) if hasattr(e, "__dict__") else None
+            if v:
+                return int(v)
+        e = e.__dict__.get("env") if hasattr(e, "__dict__") else None
+    return None
+
+
 def eval_winrate(env, model, max_states=200_000, max_episode_steps=None, seed=0):
     """(win rate, mean interactions, mean time steps) of `model` started from every non-target state, as the reference's
     eval_winrate (utils/eval.py:160-197) computes them: states in itertools.product([0, 1], repeat=N) order (node 0 most
@@ -156,7 +173,7 @@ def eval_winrate(env, model, max_states=200_000, max_episode_steps=None, seed=0)
     is called once per step when it exists, else `model.predict(obs_row, obs_row, deterministic=True)` per env."""
     from gym_PBN.b200.vector_env import PBNVectorEnv
 
-    limit = max_episode_steps if max_episode_steps is not None else getattr(env, "_max", None)
+    limit = max_episode_steps if max_episode_steps is not None else _step_limit(env)
     if not limit:
         raise ValueError("eval_winrate needs a step limit: make the env through gym_PBN.make (registered max_episode_steps) "
                          "or pass max_episode_steps")

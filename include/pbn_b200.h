@@ -139,14 +139,14 @@ int pbn_env_step_f64(const PbnEnv *env, uint32_t *state, int32_t *n_steps, const
                      const PbnDraws *draws, void *stream);
 
 /* Vector-env step: K2 plus, in the same launch, the bookkeeping a batched env needs — running episode return/length,
-   block-aggregated statistics (episodes, return sum, length sum, successes, inner-cap hits, env steps; accumulated into
-   stats[6]), the step's observation copied to final_obs, and for finished envs the reset (reset_draws, its own epoch), after
+   block-aggregated statistics (episodes, return sum, length sum, successes, inner-cap hits, env steps, env steps whose
+   intervention was out of range and therefore ignored, reserved; accumulated into stats[8]), the step's observation copied to final_obs, and for finished envs the reset (reset_draws, its own epoch), after
    which obs_state holds the NEW state of those envs.  Bit-identical to pbn_env_step followed by a masked pbn_env_reset.
    The reference has no vector env; this serves gym_PBN.b200.vector_env.PBNVectorEnv.step. */
 typedef struct {
     int64_t *ep_return;     /* [B] */
     int32_t *ep_len;        /* [B] */
-    int64_t *stats;         /* [6] */
+    int64_t *stats;         /* [8] */
     uint32_t *final_obs;    /* planes [W32][B], optional */
     uint32_t *target_state; /* planes [W32][B], written on reset (target envs) */
     int32_t autoreset;
@@ -155,6 +155,33 @@ typedef struct {
 int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
                  int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
                  int32_t *inner_steps, const PbnVecState *vec, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* Budgeted / resumable env.step of the step-until-attractor envs (PBN_ENV_TARGET, PBN_ENV_MULTI; Philox draws).  The
+   reference's inner loop `while not is_attracting_state(state): graph.step()` (pbn_target.py:270-271,
+   pbn_target_multi.py:135-146) is unbounded and heavy-tailed, and a launch lasts as long as its slowest env; with a plan, a
+   launch makes at most `budget` updates per env and PARKS the envs that are still outside every attractor: their state,
+   update count (inner_steps) and pending action cost (reward) stay in the caller's arrays, running[e] = 1, and their ids are
+   appended to a list in `work`.  A later call with resume = 1 continues exactly those envs from where they stopped (update
+   t of an env.step always takes words 2t, 2t+1 of the env's stream: pass the SAME draws as the call that began the step), so
+   a step split over k launches is bit-identical to the one-launch result.  This is also how the library itself runs a full
+   step fast: a first pass with a small budget in which every lane owns an env (most envs finish within a few updates), then
+   a resume pass without budget in which the few long-running envs are spread over the whole GPU, each run by a group of
+   lanes (gym_PBN.b200.engine.Simulator.env_step).
+     running  uint8 [B]: out, 1 = step unfinished
+     work     int32 [2 * (B + 4)]: two parking lists {count, queue head, -, -, env ids...}; list `phase` is written,
+              list `phase ^ 1` is read when resume = 1.  The call clears the header of the list it writes.
+     budget   updates per env in this launch, 0 = until every env is done (then no env is parked)
+     resume   0: every env begins a new env.step (actions applied);  1: the envs of list `phase ^ 1` continue
+   vec may be NULL (= pbn_env_step semantics) or the vector-env epilogue of pbn_vec_step, which runs when an env finishes. */
+typedef struct {
+    uint8_t *running;
+    int32_t *work;
+    int32_t budget, resume, phase;
+} PbnStepPlan;
+int pbn_env_step_plan(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
+                      int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
+                      int32_t *inner_steps, const PbnVecState *vec_or_null, const PbnStepPlan *plan, int64_t B, int64_t env0,
+                      const PbnDraws *draws, void *stream);
 
 /* reset of the envs selected by mask (NULL = all): PBNTargetEnv.reset pbn_target.py:328-352,
    PBNTargetMultiEnv.reset pbn_target_multi.py:227-259, PBNEnv.reset pbn_env.py:190-213 (+ PBN.reset common/pbn.py:55-78). */

@@ -31,7 +31,7 @@ def _worker(rank, world, port, out_dir):
     t = torch.from_numpy(h.astype(np.int64))
     pdist.allreduce_sum_(t)
     stats = pdist.EpisodeStats("cpu")
-    stats.v += torch.tensor([1, 10 * (rank + 1), 5, 1, 0, stop - start])
+    stats.v += torch.tensor([1, 10 * (rank + 1), 5, 1, 0, stop - start, 0, 0])
     red = stats.reduced()
     if rank == 0:
         np.save(os.path.join(out_dir, "hist.npy"), t.numpy())

@@ -122,3 +122,83 @@ def test_large_truth_table_rollout_and_sync(eng):
     sim.rollout(2, sync=True)
     orc.rollout(onet, ost, 2, orc.Draws(seed=seed, epoch=2), sync=True)
     assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+
+
+def _target_case(eng, name, kind, n_act, B, seed, max_inner, care=4, full_care=False):
+    """A step-until-attractor env on a shipped predictor set with a cube fixture, product + oracle side by side."""
+    net = eng.engine.Network(eng.compiler.load_bittner(name))
+    sets, ids = orc.load_bittner(name)
+    onet = orc.net_from_predictor_sets(sets, ids)
+    n = net.n
+    rng = np.random.default_rng(seed)
+    atts = []
+    for a in range(5):
+        c = ["*"] * n
+        for i in rng.choice(n, size=n if full_care and a == 0 else care, replace=False):
+            c[i] = int(rng.integers(0, 2))
+        atts.append([tuple(c)] if a else [tuple(c), tuple(1 - v if v != "*" else v for v in c)])
+    multi = kind == "multi"
+    env = eng.engine.EnvImage(net, eng.abi.ENV_MULTI if multi else eng.abi.ENV_TARGET, attractors=atts, horizon=100,
+                              max_inner=max_inner, dedup=True)
+    oenv = orc.Env(orc.ENV_MULTI if multi else orc.ENV_TARGET, n, attractors=atts, horizon=100, max_inner=max_inner, dedup=1)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost, ons, ota = np.zeros((B, n), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    acts = [rng.integers(0, n + 1, size=(B, n_act)).astype(np.int32) for _ in range(3)]
+    return net, onet, env, oenv, sim, (ost, ons, ota), acts
+
+
+@pytest.mark.parametrize("name,kind,n_act,care", [("28_15_median", "target", 1, 5), ("100_5_kmeans", "target", 1, 6),
+                                                  ("200_5_kmeans", "multi", 3, 5), ("28_15_median", "multi", 2, 6)])
+@pytest.mark.parametrize("budgets", [(32, 0), (1, 7, 64, 0), (2, 2, 500, 3, 0), (5000,)])
+def test_step_plan_split_invariance(eng, name, kind, n_act, care, budgets):
+    """A step split over budgeted launches (first pass: a lane per env; resume passes: groups of lanes, global queue) equals
+    the oracle's unsplit step bit for bit: states, observations, rewards, flags, update counts."""
+    if kind == "multi" and budgets[0] == 1:
+        budgets = (2,) + budgets[1:]
+    B, seed = 3000, 11
+    net, onet, env, oenv, sim, (ost, ons, ota), acts = _target_case(eng, name, kind, n_act, B, seed, max_inner=700, care=care)
+    for t, act in enumerate(acts):
+        sim.env_step(env, torch.from_numpy(act), budget=budgets[0])
+        parked = [int(sim.running.sum())]
+        for b in budgets[1:]:
+            sim.env_step_resume(env, budget=b)
+            parked.append(int(sim.running.sum()))
+        assert parked[-1] == 0, parked
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + t))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(sim.unpack(sim.obs_state).cpu().numpy(), obs)
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.inner.cpu().numpy(), inner)
+        assert np.array_equal(sim.terminated.cpu().numpy(), term) and np.array_equal(sim.truncated.cpu().numpy(), trunc)
+        assert np.array_equal(sim.n_steps.cpu().numpy(), ons)
+        if len(budgets) > 1:
+            assert parked[0] > 0 and inner.max() > budgets[0]  # the split actually happened
+
+
+def test_step_plan_matches_single_launch(eng):
+    """The two-pass default of Simulator.env_step against the one-launch kernel (plan_budgets = ()), cap hits included."""
+    B, seed = 20000, 5
+    res = []
+    for p1 in ((32, 256), (), (4,), (2, 2, 2, 100)):
+        net, onet, env, oenv, sim, _, acts = _target_case(eng, "28_15_median", "target", 1, B, seed, max_inner=300, care=28,
+                                                          full_care=True)
+        sim.plan_budgets = p1
+        out = []
+        for act in acts:
+            sim.env_step(env, torch.from_numpy(act))
+            out.append((sim.unpack().cpu().numpy().copy(), sim.reward.cpu().numpy().copy(), sim.inner.cpu().numpy().copy(),
+                        sim.terminated.cpu().numpy().copy()))
+        res.append(out)
+        assert out[-1][2].max() == 300  # envs that hit the cap exist
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_step_plan_errors(eng):
+    net, onet, env, oenv, sim, _, acts = _target_case(eng, "28_15_median", "multi", 2, 64, 3, max_inner=50)
+    with pytest.raises(ValueError):
+        sim.env_step(env, torch.from_numpy(acts[0]), budget=1)  # MULTI needs two updates before it can park
+    with pytest.raises(eng.abi.PbnError):
+        eng.engine.Simulator(net, 8).env_step_resume(env)

@@ -788,3 +788,45 @@ def test_vector_env_self_triggering_matches_oracle(tag):
     s = vec.stats.reduced()
     assert s["episodes"] == episodes and s["successes"] == successes and s["env_steps"] == 6 * B and episodes > 0
     assert abs(float(vec.return_sum_f64) - ret_sum) < 1e-9 * max(1.0, abs(ret_sum))
+
+
+def test_vector_env_out_of_range_actions_are_ignored_and_counted():
+    """A policy network can emit anything: an action outside [0, N] must not touch another env's state column or the staged
+    network image; the intervention is dropped (the step equals action 0) and counted in the statistics."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    z = load("b28_target_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=32)
+    B, seed = 2048, 23
+    vec_bad, vec_ok = PBNVectorEnv(env, B, seed=seed), PBNVectorEnv(env, B, seed=seed)
+    vec_bad.reset(), vec_ok.reset()
+    rng = np.random.default_rng(3)
+    n_bad = 0
+    for t in range(6):
+        act = rng.integers(0, 29, size=(B, 1)).astype(np.int32)
+        wild = act.copy()
+        sel = rng.random(B) < 0.2
+        wild[sel, 0] = rng.choice([-7, 29, 1000, -2**31, 2**31 - 1, 4096 * 33], size=int(sel.sum()))
+        act[sel, 0] = 0
+        n_bad += int(sel.sum())
+        ob, rb, tb, ub, _ = vec_bad.step(torch.from_numpy(wild))
+        oo, ro, to, uo, _ = vec_ok.step(torch.from_numpy(act))
+        assert torch.equal(ob, oo) and torch.equal(rb, ro) and torch.equal(tb, to) and torch.equal(ub, uo)
+    assert vec_bad.stats.reduced()["invalid_actions"] == n_bad and vec_ok.stats.reduced()["invalid_actions"] == 0
+
+
+def test_self_triggering_prob_is_clamped():
+    """prob = 0 would give a stop threshold of 0: with no interval cap the macro step would never end (a GPU hang)."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    env = gym_PBN.make("gym-PBN/PBN-self-triggering-v0", logic_func_data=EX5, goal_config=dict(GOAL))
+    vec = PBNVectorEnv(env, 256, seed=1)
+    vec.reset()
+    act = np.zeros((256, 2), np.int32)
+    act[:, 1] = np.random.default_rng(0).choice([0, -5, 11, 100], size=256)
+    obs, rew, term, trunc, info = vec.step(torch.from_numpy(act))
+    torch.cuda.synchronize()
+    assert int(info["interval"].min()) >= 1 and int(info["interval"].max()) < 500

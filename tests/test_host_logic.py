@@ -262,3 +262,17 @@ def test_rollout_return_and_gae_math():
             delta = float(r[t, b]) + gamma * float(v[t + 1, b]) * (not done) - float(v[t, b])
             a = delta + gamma * lam * (not done) * a
             assert abs(a - float(adv[t, b])) < 1e-4 and abs(a + float(v[t, b]) - float(target[t, b])) < 1e-4
+
+
+def test_node_compute_next_value_draws_from_numpy_global():
+    """common/node.py:2,37 — `from numpy import random`: the host-side draw is numpy.random.uniform, so a seeded replay of
+    the reference's stream gives the reference's decisions."""
+    from gym_PBN.envs.common.node import Node
+
+    node = Node([True, True, False], np.array([[0.1, 0.9], [0.5, 0.3]]), 2, "c")
+    st = np.array([1, 0, 1], bool)
+    np.random.seed(1234)
+    got = [bool(node.compute_next_value(st)) for _ in range(64)]
+    np.random.seed(1234)
+    want = [bool(np.random.uniform(0, 1) < 0.5) for _ in range(64)]
+    assert got == want and node.get_next_value_prob(st) == 0.5
