@@ -257,7 +257,8 @@ def states_to_cubes(states, n):
 def default_attractors(net, care_nodes, seed=0, exact_max_nodes=28):
     """Attractor list for an env that was not given one (the reference calls the external CABEAN tool here,
     pbn_target.py:530): exact terminal SCCs compressed to cubes when the network is small enough for the exhaustive
-    STG and has at least two attractors, otherwise the reference's sampling recipe projected on `care_nodes`."""
+    STG and has at least two attractors; beyond that the sampled + verified route (closed cube sets); the reference's
+    sampling recipe projected on `care_nodes` (no closure guarantee) only when that finds fewer than two attractors."""
     if net.n <= exact_max_nodes:
         try:
             atts = exact_attractor_cubes(net)
@@ -265,6 +266,12 @@ def default_attractors(net, care_nodes, seed=0, exact_max_nodes=28):
                 return atts, "exact"
         except ValueError:
             pass
+    try:  # sampling + verification: closed cube sets (trap spaces, cut down to exact SCCs where they can be enumerated)
+        atts, _ = verified_attractors(net, seed=seed)
+        if len(atts) >= 2:
+            return atts, "verified"
+    except (ValueError, RuntimeError):
+        pass
     return statistical_attractors(net, resets=100, steps=1000, top=4, care_nodes=care_nodes, seed=seed), "sampled"
 
 
@@ -276,3 +283,273 @@ def exact_attractor_cubes(net, list_limit=1 << 20):
             raise ValueError(f"an attractor has {a['size']} states; too many to compress into cubes (limit {list_limit})")
         atts.append(states_to_cubes(a["states"], net.n))
     return atts
+
+
+# ------------------------------------------------------------------------ sampled + VERIFIED attractors (any N)
+# Beyond ~32 nodes the state-transition graph cannot be enumerated, and the reference hands the job to the external CABEAN
+# tool (utils/get_attractors_from_cabean.py:39-54).  Here: sample states by long asynchronous rollouts on the GPU, grow each
+# sampled state into the smallest TRAP SPACE (a cube closed under every possible update) that contains it, and — when that
+# cube is small enough to enumerate — cut it down to the exact terminal strongly connected components inside it.  Every
+# cube set that is returned has been checked symbolically: each successor of each of its cubes stays inside the set.
+class SuccessorModel:
+    """What an asynchronous update of node i can produce on a cube: host-side view of a compiled NetworkSpec."""
+
+    def __init__(self, spec):
+        from . import abi
+
+        self.spec, self.n, self.first = spec, spec.n, spec.first_updatable
+        a = spec.arrays
+        self.pred = spec.kind == abi.NET_PRED
+        if self.pred:
+            off, cum = a["pr_off"], a["pr_cum"]
+            self.rows = []  # per node: list of (inputs[4], lut16) of the predictors that can be selected
+            for i in range(self.n):
+                row, prev = [], 0.0
+                for k in range(off[i], off[i + 1]):
+                    if cum[k] > prev:  # positive selection weight (bittner/base.py:94-97: first cum_k > r)
+                        row.append((tuple(int(v) for v in a["pr_in"][4 * k:4 * k + 4]), int(a["pr_lut"][k])))
+                    prev = max(prev, float(cum[k]))
+                self.rows.append(row)
+        else:
+            self.rows = []
+            for i in range(self.n):
+                ins = tuple(int(v) for v in a["tt_in"][a["tt_in_off"][i]:a["tt_in_off"][i + 1]])
+                prob = np.asarray(a["tt_prob"][a["tt_tab_off"][i]:a["tt_tab_off"][i + 1]], np.float64)
+                self.rows.append([(ins, prob)])
+
+    def outcomes(self, i, cube):
+        """-> list of (new value b, {input node: value} that the source state must satisfy) over every way node i can be
+        updated from a state of `cube` (a sequence over {0, 1, '*'}); identical constraints are merged."""
+        out = {}
+        for ins, table in self.rows[i]:
+            k = len(ins)
+            for idx in range(1 << k):
+                req, ok = {}, True
+                for q, node in enumerate(ins):  # first input = most significant bit of the table index
+                    bit = (idx >> (k - 1 - q)) & 1
+                    if cube[node] != "*" and int(cube[node]) != bit:
+                        ok = False
+                        break
+                    if req.get(node, bit) != bit:  # the same node twice among the inputs with different bits
+                        ok = False
+                        break
+                    req[node] = bit
+                if not ok:
+                    continue
+                if self.pred:
+                    vals = ((table >> idx) & 1,)
+                else:
+                    p = float(table[idx])
+                    vals = tuple(b for b, possible in ((0, p < 1.0), (1, p > 0.0)) if possible)
+                for b in vals:
+                    out.setdefault((b, tuple(sorted(req.items()))), None)
+        return [(b, dict(req)) for (b, req) in out]
+
+    def can(self, i, cube):
+        """(node i can become 0, node i can become 1) from some state of the cube."""
+        vals = {b for b, _ in self.outcomes(i, cube)}
+        return 0 in vals, 1 in vals
+
+
+def trap_space(model, state):
+    """Smallest cube that contains `state` and is closed under every asynchronous update: free every fixed node that some
+    update can flip, until nothing changes (percolation).  Nodes below first_updatable never change (common/pbn.py:90)."""
+    cube = [int(v) for v in state]
+    changed = True
+    while changed:
+        changed = False
+        for i in range(model.first, model.n):
+            if cube[i] == "*":
+                continue
+            c0, c1 = model.can(i, cube)
+            if (c1 if cube[i] == 0 else c0):
+                cube[i] = "*"
+                changed = True
+    return tuple(cube)
+
+
+def _cube_in_union(d, cubes):
+    """Is cube d contained in the union of `cubes`?  (split d on a variable some candidate fixes)"""
+    cands = [c for c in cubes if all(cv == "*" or dv == "*" or cv == dv for cv, dv in zip(c, d))]  # those that meet d
+    for c in cands:
+        if all(cv == "*" or cv == dv for cv, dv in zip(c, d)):
+            return True
+    for c in cands:
+        for v, (cv, dv) in enumerate(zip(c, d)):
+            if dv == "*" and cv != "*":
+                lo, hi = list(d), list(d)
+                lo[v], hi[v] = 0, 1
+                return _cube_in_union(tuple(lo), cands) and _cube_in_union(tuple(hi), cands)
+    return False
+
+
+def cubes_closed(model, cubes):
+    """Verification: every successor of every state of every cube lies in the union of the cubes."""
+    cubes = [tuple(c) for c in cubes]
+    for c in cubes:
+        for i in range(model.first, model.n):
+            for b, req in model.outcomes(i, c):
+                if c[i] == "*" or c[i] == b:
+                    continue  # the successor stays in c
+                d = list(c)
+                for node, bit in req.items():
+                    d[node] = bit
+                if d[i] != "*" and d[i] != c[i]:
+                    continue  # the constraint contradicts the cube on node i itself (its own value is an input)
+                d[i] = b
+                if not _cube_in_union(tuple(d), cubes):
+                    return False
+    return True
+
+
+def terminal_sccs_in_cube(model, cube, max_free=18):
+    """Exact attractors inside a closed cube with at most max_free wildcards: explicit asynchronous STG over the 2^f states,
+    strongly connected components (SciPy), those without an outgoing edge.  Returns a list of cube lists."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    free = [v for v, c in enumerate(cube) if c == "*"]
+    f = len(free)
+    if f > max_free:
+        raise ValueError(f"{f} wildcards: too many states to enumerate")
+    pos = {v: k for k, v in enumerate(free)}
+    idx = np.arange(1 << f, dtype=np.int64)
+
+    def bit_of(node):  # value of `node` in every enumerated state
+        return ((idx >> pos[node]) & 1) if node in pos else np.full(idx.shape, int(cube[node]), np.int64)
+
+    src, dst = [], []
+    for i in free:
+        if i < model.first:
+            continue
+        cur = bit_of(i)
+        for ins, table in model.rows[i]:
+            k = len(ins)
+            t = np.zeros(idx.shape, np.int64)
+            for node in ins:
+                t = (t << 1) | bit_of(node)
+            if model.pred:
+                outs = [((table >> t) & 1)]
+            else:
+                p = np.asarray(table)[t]
+                outs = [np.where(p > 0.0, 1, cur), np.where(p < 1.0, 0, cur)]
+            for o in outs:
+                ch = o != cur
+                src.append(idx[ch])
+                dst.append(idx[ch] ^ (1 << pos[i]))
+    S = np.concatenate(src) if src else np.zeros(0, np.int64)
+    D = np.concatenate(dst) if dst else np.zeros(0, np.int64)
+    g = coo_matrix((np.ones(len(S), np.int8), (S, D)), shape=(1 << f, 1 << f)).tocsr()
+    ncomp, lab = connected_components(g, directed=True, connection="strong")
+    leaves = np.ones(ncomp, bool)
+    leaves[lab[S[lab[S] != lab[D]]]] = False
+    out = []
+    for comp in np.nonzero(leaves)[0]:
+        members = idx[lab == comp]
+        cubes = []
+        for sub in states_to_cubes(members, f):  # over the free variables; embed into the full cube
+            full = list(cube)
+            for k, v in enumerate(free):
+                full[v] = sub[k]
+            cubes.append(tuple(full))
+        out.append(cubes)
+    return out
+
+
+def restricted_network(spec, cube):
+    """The network a closed cube induces on its wildcard nodes (predictor networks): fixed inputs are folded into the LUTs,
+    so the exhaustive device search (exact_attractors) can run inside a trap space of a network of any size.
+    -> (NetworkSpec over the free nodes, list of their original indices)."""
+    from . import abi
+    from .compiler import NetworkSpec
+
+    if spec.kind != abi.NET_PRED:
+        raise ValueError("restricted_network handles predictor networks")
+    a = spec.arrays
+    free = [v for v, c in enumerate(cube) if c == "*"]
+    pos = {v: k for k, v in enumerate(free)}
+    off, ins, luts, cums, sums = [0], [], [], [], []
+    for i in free:
+        for k in range(a["pr_off"][i], a["pr_off"][i + 1]):
+            src = [int(v) for v in a["pr_in"][4 * k:4 * k + 4]]
+            lut, new = int(a["pr_lut"][k]), 0
+            for idx in range(16):
+                full = 0
+                for q, node in enumerate(src):
+                    bit = (idx >> (3 - q)) & 1 if node in pos else int(cube[node])
+                    full |= bit << (3 - q)
+                new |= ((lut >> full) & 1) << idx
+            ins += [pos.get(node, 0) for node in src]  # a folded input points anywhere: the LUT no longer depends on it
+            luts.append(new)
+            cums.append(float(a["pr_cum"][k]))
+        sums.append(float(a["pr_codsum"][i]))
+        off.append(len(luts))
+    arrays = dict(pr_off=np.array(off, np.int32), pr_in=np.array(ins, np.int32), pr_lut=np.array(luts, np.uint16),
+                  pr_cum=np.array(cums, np.float64), pr_codsum=np.array(sums, np.float64))
+    return NetworkSpec(abi.NET_PRED, len(free), 0, [spec.names[v] for v in free], arrays=arrays), free
+
+
+def terminal_sccs_on_device(net, cube, list_limit=1 << 22):
+    """Exact attractors inside a closed cube with at most 28 wildcards, by the exhaustive device search on the restricted
+    network.  Returns a list of cube lists (full-length cubes)."""
+    sub, free = restricted_network(net.spec, cube)
+    out = []
+    for att in exact_attractors(engine.Network(sub, device=net.device), list_limit):
+        if att["states"] is None:
+            raise ValueError("an attractor inside the trap space is too large to list")
+        cubes = []
+        for c in states_to_cubes(att["states"], len(free)):
+            full = list(cube)
+            for k, v in enumerate(free):
+                full[v] = c[k]
+            cubes.append(tuple(full))
+        out.append(cubes)
+    return out
+
+
+def verified_attractors(net, resets=256, steps=None, seed=0, max_free_host=14, max_free_device=26):
+    """Attractors by sampling + verification, for networks of any size: `resets` uniformly random states run `steps`
+    asynchronous updates on the GPU; each distinct end state is grown into its smallest trap space (smallest first: a walker
+    that has not converged yet gives a larger one that CONTAINS attractors already found, and is dropped when it cannot be
+    enumerated); trap spaces small enough to enumerate are replaced by the exact terminal SCCs inside them — on the host up to
+    max_free_host wildcards, by the exhaustive device search on the restricted network up to max_free_device.  Every returned
+    cube set passed `cubes_closed`.
+    -> (attractors: list of cube lists, info: list of {"method", "free", "states"} per attractor)."""
+    from . import abi
+
+    steps = int(steps) if steps else 512 * net.n  # slow transients: a 200-node set needs ~1e5 updates to settle
+    sim = engine.Simulator(net, int(resets), seed=seed)
+    sim.rand_state()
+    sim.rollout(steps)
+    ends = np.unique(sim.unpack().cpu().numpy(), axis=0)
+    model = SuccessorModel(net.spec)
+    spaces = set()
+    for s in ends:
+        if not any(all(c == "*" or c == int(v) for c, v in zip(t, s)) for t in spaces):
+            spaces.add(trap_space(model, s))  # (a state inside a known trap space has its own inside it too: found by refinement)
+    atts, info, seen = [], [], set()
+
+    def contains(big, small):
+        return all(b == "*" or b == c for b, c in zip(big, small))
+
+    for t in sorted(spaces, key=lambda c: sum(v == "*" for v in c)):
+        free = sum(v == "*" for v in t)
+        if free <= max_free_host:
+            found = [(c, "exact terminal SCC inside a sampled trap space (host)") for c in terminal_sccs_in_cube(model, t, max_free_host)]
+        elif free <= max_free_device and net.spec.kind == abi.NET_PRED:
+            found = [(c, "exact terminal SCC inside a sampled trap space (device search on the restricted network)")
+                     for c in terminal_sccs_on_device(net, t)]
+        elif any(contains(t, c) for cubes in atts for c in cubes):
+            continue  # an unconverged sample: the cube holds an attractor we already have and cannot be searched for more
+        else:
+            found = [([t], "sampled trap space (closed cube; too large to enumerate)")]
+        for cubes, method in found:
+            key = tuple(sorted(cubes, key=str))
+            if key in seen:
+                continue
+            if not cubes_closed(model, cubes):
+                raise RuntimeError("internal error: an attractor candidate is not closed under the dynamics")
+            seen.add(key)
+            atts.append(list(cubes))
+            info.append({"method": method, "free": free, "states": sum(2 ** sum(v == "*" for v in c) for c in cubes)})
+    return atts, info

@@ -39,17 +39,4 @@ def cubes_to_attractors(cubes, off):
     return atts
 
 
-def synthetic_pbcn(n=1024, m=8, seed=7):
-    """configs[4]: M control nodes first (no inputs, P=0), every other node 3 inputs and c*f1 + (1-c)*f2."""
-    rng = np.random.default_rng(seed)
-    data = []
-    for i in range(n):
-        mask = np.zeros(n, bool)
-        if i < m:
-            data.append((mask, np.array(0.0), f"u{i}", True))
-            continue
-        mask[rng.choice(n, size=3, replace=False)] = True
-        f1, f2 = rng.integers(0, 2, 8), rng.integers(0, 2, 8)
-        c = float(rng.uniform(0.1, 0.9))
-        data.append((mask, (c * f1 + (1 - c) * f2).reshape(2, 2, 2), f"x{i}", False))
-    return data
+from gym_PBN.b200.synthetic import synthetic_pbcn  # noqa: E402,F401  (configs[4]: lives in the package, bench.py uses it too)
