@@ -456,9 +456,66 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_rollout(NetView nv, DrawView dv, 
 //   TARGET: pbn_target.py:328-352 — sample(all_attractors, 2), a cube of each, '*' -> randint(0,1) position by position
 //   MULTI : pbn_target_multi.py:227-259 — first attractor -> last attractor (Q14)
 //   PBN family: pbn_env.py:190-213 — an attractor with <= 10 states, a uniform state of it, state[0] = 0 (common/pbn.py:77)
+// Curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235), one probability row per env — a vector env is B
+// independent env objects of the reference, each with its own table.
+struct CurView {
+    double *prob;    // [B][n_att] or null
+    int *pair;       // [B][2] sampled (state attractor id, target attractor id)
+    int sample_pair; // 1: the sampled ids choose the attractors; 0: first -> last as the reference does (Q14), ids only recorded
+};
+// np.random.choice(range(A), size=2, replace=False, p=prob) from three uniforms (numpy legacy RandomState.choice: searchsorted
+// on the normalised cumulative sum, first occurrences kept, the found id's mass zeroed before the redraw)
+__device__ __forceinline__ void sample_pair_dev(const double *prob, int A, const double *u, int &a, int &b) {
+    double p[64], cdf[64];
+    auto draw = [&](double x) {
+        int k = 0;
+        while (k < A && cdf[k] <= x) k++;
+        return k < A ? k : A - 1;
+    };
+    auto build = [&]() {
+        double acc = 0.0;
+        for (int k = 0; k < A; k++) { acc += p[k]; cdf[k] = acc; }
+        for (int k = 0; k < A; k++) cdf[k] /= acc;
+    };
+    for (int k = 0; k < A; k++) p[k] = prob[k];
+    build();
+    a = draw(u[0]);
+    b = draw(u[1]);
+    if (a == b) {
+        p[a] = 0.0;
+        build();
+        b = draw(u[2]);
+    }
+}
+// rework_probas(episode_len) on one row
+__device__ __forceinline__ void rework_probas_dev(double *prob, int A, int s, int t, int len) {
+    const double eps = 1.0 * 1.0 / A, lo = 0.01 * 1.0 / A, hi = 0.5;
+    if (len < 20) {
+        prob[s] -= eps; prob[t] -= eps;
+        prob[s] = prob[s] > lo ? prob[s] : lo;
+        prob[t] = prob[t] > lo ? prob[t] : lo;
+    }
+    if (len >= 99) {
+        prob[s] += eps; prob[t] += eps;
+        prob[s] = prob[s] < hi ? prob[s] : hi;
+        prob[t] = prob[t] < hi ? prob[t] : hi;
+    }
+    for (int k = 0; k < A; k++) prob[k] = lo > prob[k] ? lo : prob[k];
+    // `s = sum(self.probabilities)`: CPython >= 3.12 sums floats with Neumaier compensation (bltinmodule.c: cs_add)
+    double sum = 0.0, comp = 0.0;
+    for (int k = 0; k < A; k++) {
+        const double x = prob[k], t = sum + x;
+        comp += fabs(sum) >= fabs(x) ? (sum - t) + x : (x - t) + sum;
+        sum = t;
+    }
+    if (comp != 0.0 && isfinite(comp)) sum += comp;
+    for (int k = 0; k < A; k++) prob[k] /= sum;
+}
+
 template <int MODE>
 __device__ __forceinline__ void reset_env(const NetView &nv, const EnvView &ev, const DrawView &dv, u32 *state, int *n_steps,
-                                          int *target_att, u32 *target_state, long long B, long long e, long long env0) {
+                                          int *target_att, u32 *target_state, long long B, long long e, long long env0,
+                                          const CurView cv = CurView{nullptr, nullptr, 0}) {
     const int *att_off = reinterpret_cast<const int *>(ev.img);
     const u32 *cubes = reinterpret_cast<const u32 *>(ev.img + ev.off_cubes);
     const int n = nv.n, w32 = nv.w32;
@@ -470,7 +527,19 @@ __device__ __forceinline__ void reset_env(const NetView &nv, const EnvView &ev, 
         if (ev.kind == PBN_ENV_TARGET) {  // random.sample(all_attractors, 2), pbn_target.py:333
             if constexpr (MODE == PBN_DRAW_REPLAY) { a = d.randint(0, A); b = d.randint(0, A); }
             else { a = d.randint(0, A); b = d.randint(0, A - 1); if (b >= a) b++; }
-        } else { a = 0; b = A - 1; }  // first -> last (pbn_target_multi.py:237-238)
+        } else {
+            a = 0; b = A - 1;  // first -> last (pbn_target_multi.py:237-238)
+            if constexpr (MODE == PBN_DRAW_PHILOX) {
+                if (cv.prob && A >= 2 && A <= 64) {  // the pair drawn from this env's table (:232-235), three words, always
+                    double u[3];
+                    for (int k = 0; k < 3; k++) u[k] = ((double)d.next() + 0.5) * (1.0 / 4294967296.0);
+                    int sa, sb;
+                    sample_pair_dev(cv.prob + e * A, A, u, sa, sb);
+                    cv.pair[2 * e] = sa; cv.pair[2 * e + 1] = sb;
+                    if (cv.sample_pair) { a = sa; b = sb; }
+                }
+            }
+        }
         const int cs = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
         const int ct = att_off[b] + d.randint(0, att_off[b + 1] - att_off[b]);
         const u32 *ps = cubes + (size_t)cs * w32 * 2, *pt = cubes + (size_t)ct * w32 * 2;
@@ -502,10 +571,10 @@ __device__ __forceinline__ void reset_env(const NetView &nv, const EnvView &ev, 
 template <int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_reset(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                          int *target_att, u32 *target_state, const unsigned char *mask,
-                                                         long long B, long long env0) {
+                                                         long long B, long long env0, CurView cv) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B || (mask && !mask[e])) return;
-    reset_env<MODE>(nv, ev, dv, state, n_steps, target_att, target_state, B, e, env0);
+    reset_env<MODE>(nv, ev, dv, state, n_steps, target_att, target_state, B, e, env0, cv);
 }
 
 // Vector-env epilogue of one finished env.step (fused into the step kernels): episode bookkeeping, block-aggregated
@@ -518,6 +587,7 @@ struct VecView {
     unsigned long long *stats;  // [8] episodes, return sum, length sum, successes, cap hits, env steps, ignored interventions, -
     u32 *final_obs, *target_state;
     DrawView rdv;
+    CurView cur;
 };
 template <int MODE>
 __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev, const VecView &vx, unsigned long long *s_stats,
@@ -536,8 +606,10 @@ __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev,
         atomicAdd(&s_stats[2], (unsigned long long)len);
         vx.ep_return[e] = 0;
         vx.ep_len[e] = 0;
+        if (vx.cur.prob && ev.kind == PBN_ENV_MULTI && ev.n_att >= 2)  // env.rework_probas(episode_len), then the reset draws from it
+            rework_probas_dev(vx.cur.prob + e * ev.n_att, ev.n_att, vx.cur.pair[2 * e], vx.cur.pair[2 * e + 1], len);
         if (vx.autoreset) {
-            reset_env<MODE>(nv, ev, vx.rdv, state, n_steps, target_att, vx.target_state, B, e, env0);
+            reset_env<MODE>(nv, ev, vx.rdv, state, n_steps, target_att, vx.target_state, B, e, env0, vx.cur);
             for (int w = 0; w < nv.w32; w++) obs_state[(long long)w * B + e] = state[(long long)w * B + e];  // reset envs observe their new state
         }
     } else {
@@ -1771,6 +1843,12 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         vx.enabled = 1; vx.autoreset = vec->autoreset;
         vx.ep_return = (long long *)vec->ep_return; vx.ep_len = vec->ep_len; vx.stats = (unsigned long long *)vec->stats;
         vx.final_obs = vec->final_obs; vx.target_state = vec->target_state;
+        if (vec->probabilities) {
+            if (ev.kind != PBN_ENV_MULTI || !vec->pair_ids || ev.n_att < 2 || ev.n_att > 64)
+                return fail(PBN_ERR_ARG, "a probability table needs a MULTI env with 2..64 attractors and pair_ids");
+            if (dv.mode != PBN_DRAW_PHILOX) return fail(PBN_ERR_UNSUPPORTED, "the curriculum draws its pairs from Philox words");
+            vx.cur.prob = vec->probabilities; vx.cur.pair = vec->pair_ids; vx.cur.sample_pair = vec->sample_pair != 0;
+        }
     }
     const int block = block_for(B);
     const unsigned grid = (unsigned)((B + block - 1) / block);
@@ -1871,8 +1949,24 @@ extern "C" int pbn_env_step_plan(const PbnEnv *env, uint32_t *state, int32_t *n_
                          env0, draws, vec, stream, nullptr, plan);
 }
 
+static int env_reset_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                          const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream, CurView cv);
 extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
                              const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream) {
+    return env_reset_impl(env, state, n_steps, target_att, target_state, mask, B, env0, draws, stream, CurView{nullptr, nullptr, 0});
+}
+extern "C" int pbn_env_reset_cur(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                                 const uint8_t *mask, double *probabilities, int32_t *pair_ids, int32_t sample_pair, int64_t B,
+                                 int64_t env0, const PbnDraws *draws, void *stream) {
+    if (!env || !probabilities || !pair_ids) return fail(PBN_ERR_ARG, "bad argument");
+    if (env->v.kind != PBN_ENV_MULTI || env->v.n_att < 2 || env->v.n_att > 64)
+        return fail(PBN_ERR_ARG, "a probability table needs a MULTI env with 2..64 attractors");
+    if (!draws || draws->mode != PBN_DRAW_PHILOX) return fail(PBN_ERR_UNSUPPORTED, "the curriculum draws its pairs from Philox words");
+    return env_reset_impl(env, state, n_steps, target_att, target_state, mask, B, env0, draws, stream,
+                          CurView{probabilities, pair_ids, sample_pair != 0});
+}
+static int env_reset_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                          const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream, CurView cv) {
     if (!env || !state || B < 0) return fail(PBN_ERR_ARG, "bad argument");
     const EnvView &ev = env->v;
     if (ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI) {
@@ -1891,9 +1985,9 @@ extern "C" int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_step
     const unsigned grid = (unsigned)((B + block - 1) / block);
     cudaStream_t s = (cudaStream_t)stream;
     if (dv.mode == PBN_DRAW_PHILOX)
-        k_env_reset<PBN_DRAW_PHILOX><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0);
+        k_env_reset<PBN_DRAW_PHILOX><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0, cv);
     else
-        k_env_reset<PBN_DRAW_REPLAY><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0);
+        k_env_reset<PBN_DRAW_REPLAY><<<grid, block, 0, s>>>(env->net->v, ev, dv, state, n_steps, target_att, target_state, mask, B, env0, cv);
     CK(cudaGetLastError());
     return PBN_OK;
 }

@@ -44,7 +44,8 @@ class PbnFitDesc(C.Structure):
 
 class PbnVecState(C.Structure):
     _fields_ = [("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("stats", C.c_void_p), ("final_obs", C.c_void_p),
-                ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws)]
+                ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws),
+                ("probabilities", C.c_void_p), ("pair_ids", C.c_void_p), ("sample_pair", C.c_int32)]
 
 
 class PbnStepPlan(C.Structure):
@@ -74,6 +75,8 @@ EXPORTS = {
                                     C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
+    "pbn_env_reset_cur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_rand_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(PbnDraws), C.c_void_p]),
     "pbn_ssd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
                           C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(PbnDraws), C.c_void_p]),

@@ -290,19 +290,21 @@ class Simulator:
             raise abi.PbnError("env_step_resume without a budgeted env_step")
         self._plan_call(env, self._plan_actions, self._plan_draws, budget, 1)
 
-    def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True):
+    def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True, curriculum=None):
         """Fused vector-env step (one launch): env.step for every env + episode bookkeeping + statistics + reset of the envs
         that finished.  Consumes two epochs (step, reset) exactly like env_step followed by a masked env_reset."""
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, dtype=torch.int32).contiguous()
         K = actions.numel() // self.B
         key = (env.handle.value, ep_return.data_ptr(), final_obs.data_ptr() if final_obs is not None else 0, bool(autoreset),
-               tuple(self.plan_budgets))
+               tuple(self.plan_budgets), curriculum[0].data_ptr() if curriculum else 0)
         c = self._vec_cache
         if c is None or c["key"] != key:  # the buffers never move: build the argument block once
             d, rd = abi.PbnDraws(mode=abi.DRAW_PHILOX), abi.PbnDraws(mode=abi.DRAW_PHILOX)
             v = abi.PbnVecState(ep_return=_ptr(ep_return), ep_len=_ptr(ep_len), stats=_ptr(stats), final_obs=_ptr(final_obs),
                                 target_state=_ptr(self.target_state), autoreset=int(bool(autoreset)))
+            if curriculum:  # (probabilities float64 [B][A], pair_ids int32 [B][2], sample_pair)
+                v.probabilities, v.pair_ids, v.sample_pair = _ptr(curriculum[0]), _ptr(curriculum[1]), int(bool(curriculum[2]))
             head = (env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att))
             tail = (_ptr(self.obs_state), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), _ptr(self.inner))
             c = self._vec_cache = {"key": key, "d": d, "v": v, "head": head, "tail": tail, "fn": abi.lib().pbn_vec_step}
@@ -332,10 +334,19 @@ class Simulator:
                 abi.check(rc)
             self.launches += 1
 
-    def env_reset(self, env: EnvImage, mask=None, replay=None):
+    def env_reset(self, env: EnvImage, mask=None, replay=None, curriculum=None):
+        """curriculum = (probabilities float64 [B][A], pair_ids int32 [B][2], sample_pair): PBNTargetMultiEnv draws its
+        attractor pair from the env's own probability row (pbn_target_multi.py:232-235)."""
         if mask is not None:
             mask = mask.to(self.device, dtype=torch.uint8).contiguous()
         d = self._draws(replay)
+        if curriculum:
+            with torch.cuda.device(self.device):
+                abi.check(abi.lib().pbn_env_reset_cur(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                                      _ptr(self.target_state), _ptr(mask), _ptr(curriculum[0]), _ptr(curriculum[1]),
+                                                      int(bool(curriculum[2])), self.B, self.env0, C.byref(d), _stream()))
+                self.launches += 1
+            return
         with torch.cuda.device(self.device):
             abi.check(abi.lib().pbn_env_reset(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
                                               _ptr(self.target_state), _ptr(mask), self.B, self.env0, C.byref(d), _stream()))

@@ -36,7 +36,7 @@ def _family(env):
 
 class PBNVectorEnv:
     def __init__(self, env, num_envs=None, seed=0, autoreset=True, global_num_envs=None, obs="bits", dedup=True,
-                 max_inner_steps=None, force=False, action_slots=3):
+                 max_inner_steps=None, force=False, action_slots=3, curriculum=False, sample_pair=None):
         env = getattr(env, "unwrapped", env)
         self.env = env
         self.family = _family(env)
@@ -78,6 +78,17 @@ class PBNVectorEnv:
                 horizon=env.horizon, max_inner=self.max_inner_steps, force=force, dedup=dedup)
             self.action_width = 1 if self.family == "target" else action_slots
             self.horizon = env.horizon
+        # curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235) on the device: every env keeps its own
+        # probability row (= B independent env objects of the reference); an episode's end applies rework_probas(episode
+        # length) to the row inside the step launch, and the reset draws the (state, target) attractor ids from it
+        self.probabilities = self.pair_ids = None
+        self.sample_pair = bool(getattr(env, "sample_pair", False) if sample_pair is None else sample_pair)
+        if curriculum:
+            n_att = self.image.n_att
+            if self.family != "multi" or not 2 <= n_att <= 64:
+                raise ValueError("curriculum=True needs a PBNTargetMultiEnv with 2..64 attractors")
+            self.probabilities = torch.full((self.num_envs, n_att), 1.0 / n_att, dtype=torch.float64, device=self.device)
+            self.pair_ids = torch.zeros((self.num_envs, 2), dtype=torch.int32, device=self.device)
         self.stats = pdist.EpisodeStats(self.device)
         self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64 if self.family == "st" else torch.int64,
                                      device=self.device)
@@ -104,7 +115,7 @@ class PBNVectorEnv:
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.sim.reseed(seed)
-        self.sim.env_reset(self.image)
+        self.sim.env_reset(self.image, curriculum=self._curriculum())
         self.ep_return.zero_()
         self.ep_len.zero_()
         self._needs_reset = False
@@ -123,10 +134,15 @@ class PBNVectorEnv:
             return self._step_self_triggering(actions)
         # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)
         sim.vec_step(self.image, actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
-                     autoreset=self.autoreset)
+                     autoreset=self.autoreset, curriculum=self._curriculum())
         info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state, "final_obs_packed": self.final_obs}
+        if self.probabilities is not None:
+            info["pair_ids"], info["probabilities"] = self.pair_ids, self.probabilities
         # after the launch obs_state holds the step's observation, or the NEW state for envs that were auto-reset
         return self._obs(sim.obs_state), sim.reward, sim.terminated, sim.truncated, info
+
+    def _curriculum(self):
+        return None if self.probabilities is None else (self.probabilities, self.pair_ids, self.sample_pair)
 
     def _step_self_triggering(self, actions):
         """Macro step of every env (actions int32 [B][2] = (primitive, prob) for the PBN variant, [B][1+M] = (prob, control
@@ -169,7 +185,9 @@ class PBNVectorEnv:
         s = self.sim
         return {"state": s.state.clone(), "n_steps": s.n_steps.clone(), "target_att": s.target_att.clone(),
                 "target_state": s.target_state.clone(), "seed": s.seed, "epoch": s.epoch, "env0": s.env0,
-                "ep_return": self.ep_return.clone(), "ep_len": self.ep_len.clone(), "stats": self.stats.v.clone()}
+                "ep_return": self.ep_return.clone(), "ep_len": self.ep_len.clone(), "stats": self.stats.v.clone(),
+                "probabilities": None if self.probabilities is None else self.probabilities.clone(),
+                "pair_ids": None if self.pair_ids is None else self.pair_ids.clone()}
 
     def load_state_dict(self, d):
         s = self.sim
@@ -177,6 +195,8 @@ class PBNVectorEnv:
         s.target_state.copy_(d["target_state"])
         s.seed, s.epoch, s.env0 = int(d["seed"]), int(d["epoch"]), int(d["env0"])
         self.ep_return.copy_(d["ep_return"]); self.ep_len.copy_(d["ep_len"]); self.stats.v.copy_(d["stats"])
+        if self.probabilities is not None and d.get("probabilities") is not None:
+            self.probabilities.copy_(d["probabilities"]); self.pair_ids.copy_(d["pair_ids"])
         self._needs_reset = False
 
 

@@ -278,8 +278,9 @@ class _BittnerTarget(PBNTargetEnv):
         PBNTargetEnv.__init__(self, graph, goal, render_mode, render_no_cache, name or self.NAME, reward_config,
                               end_episode_on_success, all_attractors=all_attractors, max_inner_steps=max_inner_steps)
         if not self._all_attractors:
-            # no CABEAN here: exact terminal SCCs of the asynchronous STG (N <= 28), else the reference's own sampling
-            # recipe projected on the target genes
+            # no CABEAN here: exact terminal SCCs of the asynchronous STG (N <= 28); beyond that sampled + verified closed cube
+            # sets (b200/attractors.py: verified_attractors); the reference's own sampling recipe projected on the target
+            # genes only when that route finds fewer than two attractors (attractor_source says which)
             self.all_attractors, self.attractor_source = att_tools.default_attractors(
                 self.network, self.target_node_indices, seed=seed or 0)
 

@@ -151,6 +151,14 @@ typedef struct {
     uint32_t *target_state; /* planes [W32][B], written on reset (target envs) */
     int32_t autoreset;
     PbnDraws reset_draws;
+    /* curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235), optional: one probability row per env (a vector
+       env is B independent env objects of the reference).  When an episode ends the launch applies rework_probas(episode
+       length) to the env's row, and the reset draws the (state attractor, target attractor) ids from it like
+       np.random.choice(range(A), size=2, replace=False, p=row) (three Philox words, u = (word + 0.5) / 2^32).  sample_pair = 0
+       keeps first -> last for the attractors themselves, as the reference does; 1 uses the sampled ids. */
+    double *probabilities;  /* [B][n_att], NULL = no curriculum */
+    int32_t *pair_ids;      /* [B][2] */
+    int32_t sample_pair;
 } PbnVecState;
 int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
                  int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,
@@ -187,6 +195,11 @@ int pbn_env_step_plan(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int3
    PBNTargetMultiEnv.reset pbn_target_multi.py:227-259, PBNEnv.reset pbn_env.py:190-213 (+ PBN.reset common/pbn.py:55-78). */
 int pbn_env_reset(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
                   const uint8_t *mask, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
+
+/* pbn_env_reset for PBNTargetMultiEnv with the curriculum table of PbnVecState (same draws: the three pair words come first). */
+int pbn_env_reset_cur(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, uint32_t *target_state,
+                      const uint8_t *mask, double *probabilities, int32_t *pair_ids, int32_t sample_pair, int64_t B,
+                      int64_t env0, const PbnDraws *draws, void *stream);
 
 /* Graph.genRandState base.py:368-370 */
 int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);

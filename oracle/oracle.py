@@ -244,6 +244,32 @@ def env_reset(net, env, state, n_steps, target_att, draws, mask=None, target_sta
                         _p(mask), C.c_int64(B), C.c_int64(env0), C.byref(draws.c))
 
 
+def sample_pair(prob, u):
+    """np.random.choice(range(A), size=2, replace=False, p=prob) from the uniforms u (pbn_target_multi.py:232-235)."""
+    prob = np.ascontiguousarray(prob, np.float64)
+    u = np.ascontiguousarray(u, np.float64)
+    ids = np.zeros(2, np.int32)
+    lib().orc_sample_pair.restype = C.c_int
+    used = lib().orc_sample_pair(_p(prob), C.c_int(len(prob)), _p(u), _p(ids))
+    return (int(ids[0]), int(ids[1])), int(used)
+
+
+def rework_probas(prob_row, s, t, episode_len):
+    """In place on one float64 probability row (pbn_target_multi.py:159-181)."""
+    lib().orc_rework_probas.restype = None
+    lib().orc_rework_probas(_p(prob_row), C.c_int(len(prob_row)), C.c_int(int(s)), C.c_int(int(t)), C.c_int(int(episode_len)))
+
+
+def env_reset_cur(net, env, state, n_steps, target_att, prob, pair_ids, draws, sample_pair=False, mask=None, target_state=None, env0=0):
+    B = state.shape[0]
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+    rc = lib().orc_env_reset_cur(C.byref(net.c), C.byref(env.c), _p(state), _p(n_steps), _p(target_att), _p(target_state), _p(mask),
+                                 _p(prob), _p(pair_ids), C.c_int(int(sample_pair)), C.c_int64(B), C.c_int64(env0), C.byref(draws.c))
+    if rc:
+        raise ValueError("orc_env_reset_cur: MULTI envs with 2..64 attractors, Philox draws")
+
+
 def rand_state(net, B, draws, env0=0):
     state = np.zeros((B, net.n), np.uint8)
     lib().orc_rand_state(C.byref(net.c), _p(state), C.c_int64(B), C.c_int64(env0), C.byref(draws.c))

@@ -464,6 +464,92 @@ int orc_env_step_f64(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32
    PBN/PBCN family: pbn_env.py:190-213 — attractor with <= 10 states, uniform state from it, PBN.reset forces
            state[0]=0 (common/pbn.py:77).  The reference's discarded first choice() is not drawn in PHILOX mode;
            in REPLAY mode the recorded indices are (attractor index tries..., state index). */
+/* ---- curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235) ----------------------------------------------
+   sample_pair: np.random.choice(range(A), size=2, replace=False, p=probabilities) restated (numpy legacy RandomState.choice,
+   replace=False with p): draw size - n_uniq uniforms, searchsorted(cdf, x, side='right') on the normalised cumulative sum,
+   keep the first occurrence of each value, zero the mass of what was found, repeat until two distinct ids are there.
+   u: the uniforms in the order the generator hands them out; returns how many were consumed. */
+static int ss_right(const double *cdf, int A, double x) { int k = 0; while (k < A && cdf[k] <= x) k++; return k < A ? k : A - 1; }
+int orc_sample_pair(const double *prob, int A, const double *u, int *ids) {
+    double p[64], cdf[64];
+    int used = 0, found = 0;
+    if (A > 64) A = 64;
+    for (int k = 0; k < A; k++) p[k] = prob[k];
+    while (found < 2) {
+        for (int k = 0; k < found; k++) p[ids[k]] = 0.0;
+        double acc = 0.0;
+        for (int k = 0; k < A; k++) { acc += p[k]; cdf[k] = acc; }
+        for (int k = 0; k < A; k++) cdf[k] /= acc;
+        int want = 2 - found, fresh[2], nf = 0;
+        for (int k = 0; k < want; k++) fresh[k] = ss_right(cdf, A, u[used++]);
+        for (int k = 0; k < want; k++) { /* np.unique(return_index) + sort: first occurrences, in draw order */
+            int dup = 0;
+            for (int j = 0; j < k; j++) dup |= fresh[j] == fresh[k];
+            if (!dup) ids[found + nf++] = fresh[k];
+        }
+        found += nf;
+    }
+    return used;
+}
+/* rework_probas(episode_len), pbn_target_multi.py:159-181, on one probability row */
+void orc_rework_probas(double *prob, int A, int s, int t, int episode_len) {
+    const double eps = 1.0 * 1.0 / A, lo = 0.01 * 1.0 / A, hi = 0.5;
+    if (episode_len < 20) {
+        prob[s] -= eps; prob[t] -= eps;
+        prob[s] = prob[s] > lo ? prob[s] : lo;
+        prob[t] = prob[t] > lo ? prob[t] : lo;
+    }
+    if (episode_len >= 99) {
+        prob[s] += eps; prob[t] += eps;
+        prob[s] = prob[s] < hi ? prob[s] : hi;
+        prob[t] = prob[t] < hi ? prob[t] : hi;
+    }
+    for (int k = 0; k < A; k++) prob[k] = lo > prob[k] ? lo : prob[k];
+    /* Python's sum() over floats: CPython >= 3.12 (3.12.3 here) adds with Neumaier compensation (Python/bltinmodule.c,
+       cs_add) and folds the compensation in at the end */
+    double sum = 0.0, comp = 0.0;
+    for (int k = 0; k < A; k++) {
+        const double x = prob[k], t = sum + x;
+        comp += fabs(sum) >= fabs(x) ? (sum - t) + x : (x - t) + sum;
+        sum = t;
+    }
+    if (comp != 0.0 && isfinite(comp)) sum += comp;
+    for (int k = 0; k < A; k++) prob[k] /= sum;
+}
+
+/* MULTI reset with the pair drawn from the env's own probability row (Philox: u = (word + 0.5) * 2^-32 per uniform, drawn
+   before everything else as the reference does, :232); sample_pair = 0 keeps first -> last for the attractors (Q14) and only
+   records the ids, which is what the reference does. */
+int orc_env_reset_cur(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, int32_t *target_att,
+                      uint8_t *target_state, const uint8_t *mask, double *prob, int32_t *pair_ids, int sample_pair, int64_t B,
+                      int64_t env0, const OrcDraws *dr) {
+    const int n = net->n, A = env->n_att;
+    if (env->kind != ORC_ENV_MULTI || dr->mode != ORC_PHILOX || A < 2 || A > 64) return 1;
+    for (int64_t e = 0; e < B; e++) {
+        if (mask && !mask[e]) continue;
+        Dr d; dr_init(&d, dr, e, env0 + e);
+        double u[3];
+        int ids[2];
+        for (int k = 0; k < 3; k++) u[k] = ((double)dr_u32(&d) + 0.5) * (1.0 / 4294967296.0); /* three words, always */
+        orc_sample_pair(prob + e * A, A, u, ids);
+        pair_ids[2 * e] = ids[0]; pair_ids[2 * e + 1] = ids[1];
+        const int a = sample_pair ? ids[0] : 0, b = sample_pair ? ids[1] : A - 1;
+        int cs = env->att_off[a] + dr_randint(&d, 0, env->att_off[a + 1] - env->att_off[a]);
+        int ct = env->att_off[b] + dr_randint(&d, 0, env->att_off[b + 1] - env->att_off[b]);
+        const int8_t *s = env->cube + (int64_t)cs * n, *t = env->cube + (int64_t)ct * n;
+        uint8_t *st = state + e * n;
+        for (int i = 0; i < n; i++) {
+            st[i] = (uint8_t)(s[i] == 2 ? dr_randint(&d, 0, 2) : s[i]);
+            uint8_t tv = (uint8_t)(t[i] == 2 ? dr_randint(&d, 0, 2) : t[i]);
+            if (target_state) target_state[e * n + i] = tv;
+        }
+        target_att[e] = b;
+        n_steps[e] = 0;
+        dr_done(&d, dr, e);
+    }
+    return 0;
+}
+
 int orc_env_reset(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t *n_steps, int32_t *target_att,
                   uint8_t *target_state, const uint8_t *mask, int64_t B, int64_t env0, const OrcDraws *dr) {
     const int n = net->n;

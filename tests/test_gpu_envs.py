@@ -154,7 +154,13 @@ def test_make_bittner_100_and_200_default_attractors():
 
     env = gym_PBN.make("gym-PBN/Bittner-100-v0", seed=1)
     core = env.unwrapped
-    assert core.graph.N == 100 and len(core.all_attractors) == 4 and core.horizon == 69
+    # no CABEAN here: the sampled + verified route (closed cube sets; Bittner-100: exact terminal SCCs inside 19- and 21-wildcard
+    # trap spaces, found by the exhaustive device search on the restricted network)
+    assert core.graph.N == 100 and len(core.all_attractors) >= 2 and core.horizon == 69 and core.attractor_source == "verified"
+    from gym_PBN.b200 import attractors as att_tools
+
+    model = att_tools.SuccessorModel(core.network.spec)
+    assert all(att_tools.cubes_closed(model, a) for a in core.all_attractors)
     (state, target), info = env.reset(seed=1)
     for _ in range(5):
         obs, r, term, trunc, info = env.step(0)
@@ -830,3 +836,59 @@ def test_self_triggering_prob_is_clamped():
     obs, rew, term, trunc, info = vec.step(torch.from_numpy(act))
     torch.cuda.synchronize()
     assert int(info["interval"].min()) >= 1 and int(info["interval"].max()) < 500
+
+
+@pytest.mark.parametrize("sample_pair", [False, True])
+def test_vector_env_curriculum_matches_oracle(sample_pair):
+    """Device-side curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235): every env's own probability row is
+    reworked when its episode ends and the reset draws the attractor pair from it — product (fused in the step launch) vs the
+    oracle (step, then per finished env rework_probas + reset), bit for bit, float64 rows included."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    rng = np.random.default_rng(8)
+    n = 28
+    atts = []
+    for a in range(5):
+        c = ["*"] * n
+        for i in rng.choice(n, size=3, replace=False):
+            c[i] = int(rng.integers(0, 2))
+        atts.append([tuple(c)])
+    env = gym_PBN.make("gym-PBN/BittnerMulti-28-v0", all_attractors=atts, max_inner_steps=40, horizon=25, sample_pair=sample_pair)
+    B, seed = 1500, 31
+    vec = PBNVectorEnv(env, B, seed=seed, curriculum=True, action_slots=2)
+    obs, info = vec.reset()
+    sets, ids = orc.load_bittner("28_15_median")
+    onet = orc.net_from_predictor_sets(sets, ids)
+    oenv = orc.Env(orc.ENV_MULTI, n, attractors=atts, horizon=env.unwrapped.horizon if hasattr(env, "unwrapped") else 25, max_inner=40, dedup=1)
+    ost, ons, ota = np.zeros((B, n), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    prob = np.full((B, 5), 0.2)
+    pair = np.zeros((B, 2), np.int32)
+    orc.env_reset_cur(onet, oenv, ost, ons, ota, prob, pair, orc.Draws(seed=seed, epoch=0), sample_pair=sample_pair)
+    assert np.array_equal(obs.cpu().numpy(), ost) and np.array_equal(vec.pair_ids.cpu().numpy(), pair)
+    assert np.array_equal(vec.sim.target_att.cpu().numpy(), ota)
+    ep_len = np.zeros(B, np.int64)
+    ends = 0
+    for t in range(60):
+        act = rng.integers(0, n + 1, size=(B, 2)).astype(np.int32)
+        obs, rew, term, trunc, info = vec.step(torch.from_numpy(act))
+        oobs, orew, oterm, otrunc, oin = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + 2 * t))
+        assert np.array_equal(rew.cpu().numpy(), orew) and np.array_equal(term.cpu().numpy(), oterm.astype(bool))
+        ep_len += 1
+        done = (oterm | otrunc).astype(np.uint8)
+        for e in np.nonzero(done)[0]:
+            orc.rework_probas(prob[e], pair[e, 0], pair[e, 1], int(ep_len[e]))
+        ep_len[done.astype(bool)] = 0
+        ends += int(done.sum())
+        orc.env_reset_cur(onet, oenv, ost, ons, ota, prob, pair, orc.Draws(seed=seed, epoch=2 + 2 * t), sample_pair=sample_pair, mask=done)
+        # MULTI observes the state captured before its last update (Q11); envs that were reset observe their new state
+        assert np.array_equal(obs.cpu().numpy(), np.where(done[:, None].astype(bool), ost, oobs))
+        assert np.array_equal(vec.sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(vec.pair_ids.cpu().numpy(), pair) and np.array_equal(vec.sim.target_att.cpu().numpy(), ota)
+        assert np.array_equal(vec.probabilities.cpu().numpy(), prob)  # float64, bit for bit
+    assert ends > B and not np.allclose(prob, 0.2)  # episodes ended and the tables moved
+    sd = vec.state_dict()
+    vec2 = PBNVectorEnv(env, B, seed=0, curriculum=True, action_slots=2)
+    vec2.load_state_dict(sd)
+    act = torch.from_numpy(rng.integers(0, n + 1, size=(B, 2)).astype(np.int32))
+    assert torch.equal(vec.step(act)[0].clone(), vec2.step(act)[0]) and torch.equal(vec.probabilities, vec2.probabilities)

@@ -3,6 +3,7 @@ unmodified reference (oracle/make_golden.py).  Bit-exact: states, observations, 
 and the number of draws consumed."""
 import numpy as np
 import pytest
+from pathlib import Path
 
 import oracle as orc
 from golden_util import Traj, cubes_to_attractors, load, pbn_data_from
@@ -189,3 +190,92 @@ def test_oracle_self_triggering_envs(tag):
         assert int(inner[0]) == n and tuple(d.used[0]) == (n, 2 * n), k
         assert np.array_equal(obs[0], z[f"{tag}_obs"][k]) and bool(term[0]) == bool(z[f"{tag}_term"][k]), k
         assert rf[0] == z[f"{tag}_reward"][k], (k, rf[0], z[f"{tag}_reward"][k])
+
+
+def test_curriculum_restatements_match_numpy_and_the_reference_arithmetic():
+    """pbn_target_multi.py:232-235 — np.random.choice(range(A), size=2, replace=False, p) restated from its uniforms, checked
+    against NumPy's own legacy generator (third-party arithmetic not under /root/reference); and
+    rework_probas (:159-181) against the same float64 expressions written out in Python, the language of the reference."""
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        A = int(rng.integers(2, 9))
+        p = rng.random(A)
+        p[rng.random(A) < 0.2] *= 1e-3
+        p /= p.sum()
+        seed = int(rng.integers(0, 2**31))
+        np.random.seed(seed)
+        want = tuple(int(v) for v in np.random.choice(range(A), size=2, replace=False, p=p))
+        np.random.seed(seed)
+        u = list(np.random.random_sample(2)) + list(np.random.random_sample(1)) + list(np.random.random_sample(1))
+        got, used = orc.sample_pair(p, u)
+        assert got == want and used in (2, 3)
+
+    def reference_rework(prob, s, t, episode_len):  # the reference's statements, one for one
+        A = len(prob)
+        proba_eps = 1 * 1 / A
+        min_prob = 0.01 * 1 / A
+        max_prob = 0.5
+        if episode_len < 20:
+            prob[s] -= proba_eps
+            prob[t] -= proba_eps
+            prob[s] = max(prob[s], min_prob)
+            prob[t] = max(prob[t], min_prob)
+        if episode_len >= 99:
+            prob[s] += proba_eps
+            prob[t] += proba_eps
+            prob[s] = min(prob[s], max_prob)
+            prob[t] = min(prob[t], max_prob)
+        for i in range(len(prob)):
+            prob[i] = max(min_prob, prob[i])
+        total = sum(prob)
+        for i in range(len(prob)):
+            prob[i] /= total
+        return prob
+
+    for A in (2, 3, 7, 12):
+        mine, ref = np.full(A, 1.0 / A), [1.0 / A] * A
+        for _ in range(300):
+            s, t = (int(v) for v in rng.choice(A, 2, replace=False))
+            ln = int(rng.choice([3, 19, 20, 50, 98, 99, 100]))
+            orc.rework_probas(mine, s, t, ln)
+            ref = reference_rework(ref, s, t, ln)
+            assert mine.tolist() == ref  # bit for bit
+
+
+def test_rework_probas_against_the_unmodified_reference():
+    """The same comparison with the reference's own method object (container only: the GPU box has no /root/reference)."""
+    import os
+    import types
+
+    if not os.path.isdir("/root/reference/gym_PBN"):
+        pytest.skip("reference not present")
+    import subprocess
+    import sys
+    import json as _json
+
+    # a separate interpreter: the reference package has the same import name as the product
+    code = r"""
+import sys, json, types, numpy as np
+sys.path.insert(0, 'oracle')
+import ref_loader
+ns = ref_loader.load()
+rng = np.random.default_rng(5)
+out = []
+for A in (2, 5, 7):
+    o = types.SimpleNamespace(attractor_count=A, probabilities=[1.0 / A] * A, state_attractor_id=0, target_attractor_id=1)
+    for _ in range(100):
+        s, t = (int(v) for v in rng.choice(A, 2, replace=False))
+        ln = int(rng.choice([3, 19, 20, 50, 98, 99, 100]))
+        o.state_attractor_id, o.target_attractor_id = s, t
+        ns.pbn_target_multi.PBNTargetMultiEnv.rework_probas(o, ln)
+        out.append([A, s, t, ln, [float(p).hex() for p in o.probabilities]])
+print(json.dumps(out))
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(Path(__file__).resolve().parent.parent))
+    assert res.returncode == 0, res.stderr[-500:]
+    rows = _json.loads(res.stdout.strip().splitlines()[-1])
+    mine = {}
+    for A, s, t, ln, hexes in rows:
+        row = mine.setdefault(A, np.full(A, 1.0 / A))
+        orc.rework_probas(row, s, t, ln)
+        assert [float(v).hex() for v in row] == hexes
