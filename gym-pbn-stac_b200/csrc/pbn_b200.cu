@@ -280,6 +280,11 @@ __device__ __forceinline__ void store_state(const Col &c, u32 *g, long long B, l
     for (int w = 0; w < w32; w++) g[(long long)w * B + e] = c.word(w);
 }
 
+// the launch's epoch when it lives (partly) in device memory: epoch + *epoch_ptr
+__device__ __forceinline__ void resolve_epoch(DrawView &dv) {
+    if (dv.epoch_ptr) dv.epoch += *dv.epoch_ptr;
+}
+
 // An intervention on node `pos`; an index outside the network (a policy network can emit anything) is ignored and counted —
 // it must not flip a bit of a neighbouring env's column or of the staged network image.
 __device__ __forceinline__ void flip_node(const Col &st, int pos, int n, int &bad) {
@@ -382,6 +387,7 @@ static DrawView make_draws(const PbnDraws *d) {
         v.rk[2 * r + 1] = v.seed_hi + (u32)r * 0xBB67AE85u;
     }
     v.used = (long long *)d->used;
+    v.epoch_ptr = d->epoch_dev;
     return v;
 }
 
@@ -574,6 +580,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_reset(NetView nv, EnvView ev,
                                                          long long B, long long env0, CurView cv) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B || (mask && !mask[e])) return;
+    resolve_epoch(dv);
     reset_env<MODE>(nv, ev, dv, state, n_steps, target_att, target_state, B, e, env0, cv);
 }
 
@@ -750,6 +757,8 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
                                                         int *reward, unsigned char *terminated, unsigned char *truncated,
                                                         int *inner_steps, long long B, long long env0, VecView vx, double *rew_f64) {
+    resolve_epoch(dv);
+    resolve_epoch(vx.rdv);
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
@@ -960,6 +969,8 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
                                                             int *inner_steps, long long B, long long env0, long long per_block,
                                                             int coop_on, int grp_mode, PlanView pl, VecView vx) {
+    resolve_epoch(dv);
+    resolve_epoch(vx.rdv);
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
@@ -1170,6 +1181,8 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
                                                               int *target_att, const int *actions, int K, u32 *obs_state,
                                                               int *reward, unsigned char *terminated, unsigned char *truncated,
                                                               int *inner_steps, long long B, long long env0, PlanView pl, VecView vx) {
+    resolve_epoch(dv);
+    resolve_epoch(vx.rdv);
     unsigned char *blob = smem_raw;
     unsigned char *img = smem_raw + nv.blob_bytes;
     u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
@@ -1895,7 +1908,9 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                    \
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD, TQ>, block, smem));         \
         long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
-        const int grp_mode = coop_on && NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && ev.n_att > 0 && !ev.force; \
+        /* group mode pays when env.steps can be long; under a small cap a lane per env (4x the envs in flight) is faster */ \
+        const int grp_mode = coop_on && NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && ev.n_att > 0 && !ev.force && \
+                             (ev.max_inner > 64 || pl.resume);                                                    \
         const long long cap_grid = grp_mode ? (B + PBN_BLOCK / 4 - 1) / (PBN_BLOCK / 4) : (long long)grid;        \
         if (pgrid > cap_grid) pgrid = cap_grid;  /* (a resume pass learns its env count on the device) */         \
         const long long per_block = (B + pgrid - 1) / pgrid;                                                      \

@@ -61,6 +61,7 @@ struct DrawView {
     const double *dbls;
     long long int_stride, dbl_stride;
     long long *used;
+    const u32 *epoch_ptr;  // optional: the launch's epoch is epoch + *epoch_ptr (CUDA-graph replays, see PbnDraws.epoch_dev)
     // Philox round keys (rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85), computed once on the host:
     // read from the kernel-parameter bank they are immediate operands of the round's XOR instead of ten key updates per block
     u32 rk[20];

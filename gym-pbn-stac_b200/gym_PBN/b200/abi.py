@@ -34,7 +34,7 @@ class PbnEnvDesc(C.Structure):
 class PbnDraws(C.Structure):
     _fields_ = [("mode", C.c_int32), ("epoch", C.c_uint32), ("seed", C.c_uint64),
                 ("ints", C.c_void_p), ("dbls", C.c_void_p), ("int_stride", C.c_int64), ("dbl_stride", C.c_int64),
-                ("used", C.c_void_p)]
+                ("used", C.c_void_p), ("epoch_dev", C.c_void_p)]
 
 
 class PbnFitDesc(C.Structure):

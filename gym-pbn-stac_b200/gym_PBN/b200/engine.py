@@ -290,7 +290,8 @@ class Simulator:
             raise abi.PbnError("env_step_resume without a budgeted env_step")
         self._plan_call(env, self._plan_actions, self._plan_draws, budget, 1)
 
-    def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True, curriculum=None):
+    def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True, curriculum=None,
+                 epoch_dev=None, epoch_base=None):
         """Fused vector-env step (one launch): env.step for every env + episode bookkeeping + statistics + reset of the envs
         that finished.  Consumes two epochs (step, reset) exactly like env_step followed by a masked env_reset."""
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
@@ -315,9 +316,13 @@ class Simulator:
                 c["fn2"] = abi.lib().pbn_env_step_plan
         d, v = c["d"], c["v"]
         d.seed = v.reset_draws.seed = self.seed
-        d.epoch = self.epoch & 0xFFFFFFFF
         v.reset_draws.mode = abi.DRAW_PHILOX
-        v.reset_draws.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        if epoch_dev is not None:  # CUDA-graph capture: the epoch is epoch_base + a counter in device memory (int32 [1])
+            d.epoch, v.reset_draws.epoch = epoch_base & 0xFFFFFFFF, (epoch_base + 1) & 0xFFFFFFFF
+            d.epoch_dev = v.reset_draws.epoch_dev = _ptr(epoch_dev)
+        else:
+            d.epoch, v.reset_draws.epoch = self.epoch & 0xFFFFFFFF, (self.epoch + 1) & 0xFFFFFFFF
+            d.epoch_dev = v.reset_draws.epoch_dev = None
         self.epoch += 2
         with on_device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

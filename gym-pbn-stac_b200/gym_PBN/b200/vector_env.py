@@ -36,7 +36,7 @@ def _family(env):
 
 class PBNVectorEnv:
     def __init__(self, env, num_envs=None, seed=0, autoreset=True, global_num_envs=None, obs="bits", dedup=True,
-                 max_inner_steps=None, force=False, action_slots=3, curriculum=False, sample_pair=None):
+                 max_inner_steps=None, force=False, action_slots=3, curriculum=False, sample_pair=None, cuda_graph=False):
         env = getattr(env, "unwrapped", env)
         self.env = env
         self.family = _family(env)
@@ -89,6 +89,11 @@ class PBNVectorEnv:
                 raise ValueError("curriculum=True needs a PBNTargetMultiEnv with 2..64 attractors")
             self.probabilities = torch.full((self.num_envs, n_att), 1.0 / n_att, dtype=torch.float64, device=self.device)
             self.pair_ids = torch.zeros((self.num_envs, 2), dtype=torch.int32, device=self.device)
+        # cuda_graph=True: from its second call on, step() replays ONE captured CUDA graph (the step launches, the observation
+        # unpack, the epoch increment) instead of issuing the launches from Python — the Philox epoch then lives in device
+        # memory (PbnDraws.epoch_dev).  Same results, bit for bit; actions are copied into a buffer the graph reads.
+        self.cuda_graph = bool(cuda_graph) and self.family != "st"
+        self._graph = None
         self.stats = pdist.EpisodeStats(self.device)
         self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64 if self.family == "st" else torch.int64,
                                      device=self.device)
@@ -96,6 +101,7 @@ class PBNVectorEnv:
         self.ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self.final_obs = torch.zeros_like(self.sim.state)
         self._needs_reset = True
+        self._warm = False
         self._obs_bits = None
 
     # ---- observations -----------------------------------------------------------------------------------------
@@ -132,14 +138,50 @@ class PBNVectorEnv:
         sim = self.sim
         if self.family == "st":
             return self._step_self_triggering(actions)
-        # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)
-        sim.vec_step(self.image, actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
-                     autoreset=self.autoreset, curriculum=self._curriculum())
         info = {"inner_steps": sim.inner, "packed_obs": sim.obs_state, "final_obs_packed": self.final_obs}
         if self.probabilities is not None:
             info["pair_ids"], info["probabilities"] = self.pair_ids, self.probabilities
+        if self.cuda_graph and self._warm:
+            return self._step_graph(actions), sim.reward, sim.terminated, sim.truncated, info
+        # one fused launch: step + episode bookkeeping + statistics (+ reset of finished envs, own Philox epoch)
+        sim.vec_step(self.image, actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
+                     autoreset=self.autoreset, curriculum=self._curriculum())
+        self._warm = True
         # after the launch obs_state holds the step's observation, or the NEW state for envs that were auto-reset
         return self._obs(sim.obs_state), sim.reward, sim.terminated, sim.truncated, info
+
+    @property
+    def action_buffer(self):
+        """cuda_graph=True, after the graph exists: the int32 [num_envs][action_width] device tensor the captured step reads.
+        A policy that writes its actions there and passes the same tensor to step() saves the copy."""
+        return self._g_actions if self._graph is not None else None
+
+    def _step_graph(self, actions):
+        sim = self.sim
+        actions = actions.to(self.device, dtype=torch.int32).reshape(self.num_envs, self.action_width)
+        if self._graph is None:  # capture (the eager call before this one was the warm-up)
+            self._g_actions = actions.clone().contiguous()
+            self._g_epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._g_base = self._g_next = sim.epoch
+            launches0, epoch0 = sim.launches, sim.epoch
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sim.vec_step(self.image, self._g_actions, self.ep_return, self.ep_len, self.stats.v, final_obs=self.final_obs,
+                             autoreset=self.autoreset, curriculum=self._curriculum(), epoch_dev=self._g_epoch, epoch_base=self._g_base)
+                self._g_obs = self._obs(sim.obs_state)
+                self._g_epoch += 2
+            self._g_launches = sim.launches - launches0
+            sim.launches, sim.epoch = launches0, epoch0  # capturing ran nothing
+            self._graph = g
+        elif actions.data_ptr() != self._g_actions.data_ptr():  # write into `action_buffer` to skip this copy
+            self._g_actions.copy_(actions)
+        if sim.epoch != self._g_next:  # epochs were consumed outside the graph (reset, load_state_dict): re-base the counter
+            self._g_epoch.fill_(sim.epoch - self._g_base)
+        self._graph.replay()
+        sim.epoch += 2
+        sim.launches += self._g_launches
+        self._g_next = sim.epoch
+        return self._g_obs
 
     def _curriculum(self):
         return None if self.probabilities is None else (self.probabilities, self.pair_ids, self.sample_pair)

@@ -112,6 +112,9 @@ typedef struct {
     const double *dbls;  /* device */
     int64_t int_stride, dbl_stride;
     int64_t *used; /* device, optional [B][2]: draws consumed per env */
+    const uint32_t *epoch_dev; /* device, optional: the launch uses epoch + *epoch_dev.  Lets a captured CUDA graph of an
+                                  env.step advance its Philox epoch from device memory between replays (honoured by the env
+                                  step / reset entry points: pbn_env_step*, pbn_vec_step, pbn_env_step_plan, pbn_env_reset*) */
 } PbnDraws;
 
 /* K1 — `steps` updates of B envs in one launch, state resident on chip.

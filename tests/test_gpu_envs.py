@@ -892,3 +892,36 @@ def test_vector_env_curriculum_matches_oracle(sample_pair):
     vec2.load_state_dict(sd)
     act = torch.from_numpy(rng.integers(0, n + 1, size=(B, 2)).astype(np.int32))
     assert torch.equal(vec.step(act)[0].clone(), vec2.step(act)[0]) and torch.equal(vec.probabilities, vec2.probabilities)
+
+
+@pytest.mark.parametrize("family", ["target", "multi"])
+def test_vector_env_cuda_graph_step_is_bit_identical(family):
+    """cuda_graph=True: step() replays one captured graph (the planned step launches + unpack + epoch increment, epoch in
+    device memory) — same observations, rewards, flags and statistics as the eager env, resets and reloads in between."""
+    import gym_PBN
+    from gym_PBN.b200.vector_env import PBNVectorEnv
+
+    z = load("b28_target_env.npz" if family == "target" else "b28_multi_env.npz")
+    atts = cubes_to_attractors(z["att_cubes"], z["att_off"])
+    env = gym_PBN.make("gym-PBN/Bittner-28-v0" if family == "target" else "gym-PBN/BittnerMulti-28-v0", all_attractors=atts,
+                       max_inner_steps=200)
+    B, seed = 3000, 5
+    kw = dict(curriculum=True, action_slots=2) if family == "multi" else {}
+    a, b = PBNVectorEnv(env, B, seed=seed, **kw), PBNVectorEnv(env, B, seed=seed, cuda_graph=True, **kw)
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+    assert torch.equal(oa, ob)
+    rng = np.random.default_rng(1)
+    width = a.action_width
+    for t in range(12):
+        act = torch.from_numpy(rng.integers(0, 29, size=(B, width)).astype(np.int32))
+        ra, rb = a.step(act), b.step(act)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y), t
+        assert torch.equal(ra[4]["inner_steps"], rb[4]["inner_steps"])
+        if t == 5:  # epochs consumed outside the graph
+            assert torch.equal(a.reset()[0], b.reset()[0])
+        if t == 8:
+            sd = a.state_dict()
+            a.load_state_dict(sd), b.load_state_dict(sd)
+    assert b._graph is not None and a.stats.reduced() == b.stats.reduced() and a.sim.epoch == b.sim.epoch

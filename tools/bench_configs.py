@@ -84,18 +84,22 @@ def main():
     from gym_PBN.b200.vector_env import PBNVectorEnv
 
     genv = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=[[("*",) * 28], [("*",) * 28]], max_inner_steps=1)
-    for obs_mode in ("bits", "packed"):
-        vec = PBNVectorEnv(genv, 65536, seed=1, obs=obs_mode)
+    for obs_mode, graph in (("bits", False), ("packed", False), ("bits", True), ("packed", True)):
+        vec = PBNVectorEnv(genv, 65536, seed=1, obs=obs_mode, cuda_graph=graph)
         vec.reset()
         for _ in range(20):
             vec.step(acts)
+        a_in = acts
+        if graph:  # the policy writes straight into the buffer the captured graph reads
+            a_in = vec.action_buffer
+            a_in.copy_(acts)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(200):
-            vec.step(acts)
+            vec.step(a_in)
         torch.cuda.synchronize()
         t = (time.perf_counter() - t0) / 200
-        out.append({"config": f"PBNVectorEnv.step wall clock, Bittner-28, 65536 envs, all-attracting, obs={obs_mode}",
+        out.append({"config": f"PBNVectorEnv.step wall clock, Bittner-28, 65536 envs, all-attracting, obs={obs_mode}, cuda_graph={graph}",
                     "env_steps_per_s": 65536 / t, "us_per_step": t * 1e6})
     # configs[3]: Bittner-200 target_multi, attractor path, 131 072 envs per GPU
     net = engine.Network(compiler.load_bittner("200_5_kmeans"))
