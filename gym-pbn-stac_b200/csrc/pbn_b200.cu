@@ -549,17 +549,34 @@ __device__ __forceinline__ void reset_env(const NetView &nv, const EnvView &ev, 
         const int cs = att_off[a] + d.randint(0, att_off[a + 1] - att_off[a]);
         const int ct = att_off[b] + d.randint(0, att_off[b + 1] - att_off[b]);
         const u32 *ps = cubes + (size_t)cs * w32 * 2, *pt = cubes + (size_t)ct * w32 * 2;
-        u32 sw = 0, tw = 0;
-        for (int i = 0; i < n; i++) {  // '*' -> randint(0,1), state then target, position by position (:336-340)
-            const int w = i >> 5, bit = i & 31;
-            u32 sv = ((ps[2 * w] >> bit) & 1u) ? ((ps[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
-            u32 tv = ((pt[2 * w] >> bit) & 1u) ? ((pt[2 * w + 1] >> bit) & 1u) : (u32)d.randint(0, 2);
-            sw |= sv << bit; tw |= tv << bit;
-            if (bit == 31 || i == n - 1) {
-                state[(long long)w * B + e] = sw;
-                if (target_state) target_state[(long long)w * B + e] = tw;
-                sw = tw = 0;
+        // '*' -> randint(0,1), state then target, position by position (:336-340).  Replay: one recorded draw per '*'.
+        // Philox: the wildcards take the BITS of the stream's words in that same order, most significant first (32 per word
+        // instead of one word each: a 199-node reset with 120-wildcard cubes is 8 words, not 240), and only positions that
+        // have a wildcard are visited.
+        u32 bitbuf = 0;
+        int nbits = 0;
+        auto wild = [&]() -> u32 {
+            if constexpr (MODE == PBN_DRAW_PHILOX) {
+                if (nbits == 0) { bitbuf = d.next(); nbits = 32; }
+                nbits--;
+                const u32 v = bitbuf >> 31;
+                bitbuf <<= 1;
+                return v;
+            } else {
+                return (u32)d.randint(0, 2);
             }
+        };
+        for (int w = 0; w < w32; w++) {
+            const u32 valid = (w == w32 - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
+            const u32 sc = ps[2 * w], tc = pt[2 * w];
+            u32 sw = ps[2 * w + 1] & sc, tw = pt[2 * w + 1] & tc;
+            for (u32 m = (~sc | ~tc) & valid; m != 0u; m &= m - 1u) {
+                const u32 bit = m & (0u - m);
+                if (!(sc & bit)) sw |= wild() ? bit : 0u;
+                if (!(tc & bit)) tw |= wild() ? bit : 0u;
+            }
+            state[(long long)w * B + e] = sw;
+            if (target_state) target_state[(long long)w * B + e] = tw;
         }
         target_att[e] = b;
         n_steps[e] = 0;

@@ -130,6 +130,17 @@ static inline int dr_randint(Dr *d, int lo, int n) {
     return lo + (int)(((uint64_t)dr_u32(d) * (uint32_t)n) >> 32);
 }
 static inline double dr_dbl(Dr *d) { d->nd++; return *d->dp++; }
+/* '*' -> randint(0,1) of a reset: replay = one recorded draw each; Philox = the bits of the stream's words, most significant
+   first, 32 wildcards per word */
+typedef struct { uint32_t buf; int n; } WildBits;
+static inline int dr_wild(Dr *d, WildBits *wb) {
+    if (d->mode == ORC_REPLAY) return dr_randint(d, 0, 2);
+    if (wb->n == 0) { wb->buf = dr_u32(d); wb->n = 32; }
+    wb->n--;
+    int v = (int)(wb->buf >> 31);
+    wb->buf <<= 1;
+    return v;
+}
 static inline uint32_t thr31(double p) { /* smallest T with (r31 < T) <=> (r31 / 2^31 < p) */
     double t = ceil(p * 2147483648.0);
     if (!(t > 0)) return 0;
@@ -538,9 +549,10 @@ int orc_env_reset_cur(const OrcNet *net, const OrcEnv *env, uint8_t *state, int3
         int ct = env->att_off[b] + dr_randint(&d, 0, env->att_off[b + 1] - env->att_off[b]);
         const int8_t *s = env->cube + (int64_t)cs * n, *t = env->cube + (int64_t)ct * n;
         uint8_t *st = state + e * n;
+        WildBits wb = {0, 0};
         for (int i = 0; i < n; i++) {
-            st[i] = (uint8_t)(s[i] == 2 ? dr_randint(&d, 0, 2) : s[i]);
-            uint8_t tv = (uint8_t)(t[i] == 2 ? dr_randint(&d, 0, 2) : t[i]);
+            st[i] = (uint8_t)(s[i] == 2 ? dr_wild(&d, &wb) : s[i]);
+            uint8_t tv = (uint8_t)(t[i] == 2 ? dr_wild(&d, &wb) : t[i]);
             if (target_state) target_state[e * n + i] = tv;
         }
         target_att[e] = b;
@@ -566,9 +578,10 @@ int orc_env_reset(const OrcNet *net, const OrcEnv *env, uint8_t *state, int32_t 
             int cs = env->att_off[a] + dr_randint(&d, 0, env->att_off[a + 1] - env->att_off[a]);
             int ct = env->att_off[b] + dr_randint(&d, 0, env->att_off[b + 1] - env->att_off[b]);
             const int8_t *s = env->cube + (int64_t)cs * n, *t = env->cube + (int64_t)ct * n;
+            WildBits wb = {0, 0};
             for (int i = 0; i < n; i++) {
-                st[i] = (uint8_t)(s[i] == 2 ? dr_randint(&d, 0, 2) : s[i]);
-                uint8_t tv = (uint8_t)(t[i] == 2 ? dr_randint(&d, 0, 2) : t[i]);
+                st[i] = (uint8_t)(s[i] == 2 ? dr_wild(&d, &wb) : s[i]);
+                uint8_t tv = (uint8_t)(t[i] == 2 ? dr_wild(&d, &wb) : t[i]);
                 if (target_state) target_state[e * n + i] = tv;
             }
             target_att[e] = b;
