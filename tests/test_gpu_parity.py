@@ -515,6 +515,40 @@ def test_ssd_total_variation_vs_reference_gpu(eng):
     print("TV floor", floor, "gpu-vs-refA", _tv(hist, ref_a), "gpu(big)-vs-pooled", _tv(hb, pooled))
 
 
+def _batch_se(batches):
+    """Per-bucket standard error of the pooled estimate from independent batch estimates."""
+    p = batches / batches.sum(1, keepdims=True)
+    return p.std(0, ddof=1) / np.sqrt(len(batches))
+
+
+def test_ssd_tight_tolerance_vs_literal_reference_algorithm(eng):
+    """The product's SSD (geometric-skip flips, 31-bit integer thresholds, Philox) against 1.024e9 iterations of the
+    reference's LITERAL algorithm — N Bernoulli(p) draws per iteration with float64 compares, `u*CODsum < cum` predictor
+    picks — run through the oracle's replay path on NumPy draws (oracle/make_ssd_literal_golden.py; that path is pinned to
+    traces of the unmodified reference).  Same chain length (4 000, the reference's default), 1.05e9 GPU iterations.
+    Tolerance: total variation <= 0.005 over the 128 buckets (measured: 0.0009; round 1 accepted 0.094), and no bucket further
+    than 5 standard errors (batch means on both sides) from the literal estimate."""
+    z = load("b100_ssd_literal.npz")
+    lit = z["hist"].astype(np.float64)
+    iters = int(z["iters"])
+    net = eng.engine.Network(eng.compiler.load_bittner(str(z["pickle"])))
+    tgt = z["tgt_nodes"].astype(np.int32)
+    runs = []
+    for k in range(8):
+        sim = eng.engine.Simulator(net, 1 << 15, seed=100 + k)
+        sim.rand_state()
+        runs.append(sim.ssd(iters, float(z["p"]), tgt).cpu().numpy().astype(np.float64))
+    gpu = np.array(runs)
+    assert gpu.sum() == 8 * (1 << 15) * iters
+    tv = _tv(gpu.sum(0), lit.sum(0))
+    p_lit, p_gpu = lit.sum(0) / lit.sum(), gpu.sum(0) / gpu.sum()
+    se = np.sqrt(_batch_se(lit) ** 2 + _batch_se(gpu) ** 2)
+    zmax = float(np.max(np.abs(p_gpu - p_lit)[p_lit > 1e-3] / se[p_lit > 1e-3]))
+    print("TV(gpu 1.05e9, literal 1.02e9) =", tv, "max |z| =", zmax)
+    assert tv <= 0.005
+    assert zmax <= 5.0
+
+
 def test_ssd_split_invariance(eng):
     """Shards cut at multiples of 32 chains reproduce the one-launch estimate exactly (the multi-GPU contract: groups of
     32 consecutive global chain ids share one perturbation stream)."""
