@@ -376,6 +376,38 @@ __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb
 
 #include "pbn_coop.cuh"
 
+// the same update, predicated (`on`) and reporting the node, the old and the new word — for callers that track the state
+// incrementally (the lockstep first pass of the step-until-attractor envs keeps per-cube mismatch counts)
+template <int TQ>
+__device__ __forceinline__ void fast_update_io(const SsdFast &f, u32 wa, u32 wb, bool on, u32 &i, u32 &old, u32 &nw) {
+    i = __umulhi(wa, f.n);
+    const u32 r = wb >> 1;
+    u32 j16;
+    if constexpr (TQ == 1) {
+        j16 = count_le_x16(ldc_v4(f.thr + i * f.thr_stride), r);
+    } else {
+        const uint4 m = ldc_v4(f.thr + i * f.thr_stride);
+        u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
+        q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
+        j16 = 64u * q + count_le_x16(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
+    }
+    const uint4 rec = ldc_v4(f.rec + i * f.rec_stride + j16);
+    const u32 f1 = rec.x >> 16, f3 = rec.y >> 16;
+    const u32 w0 = lds_u32(f.col | (rec.x & 0x1C00u));
+    const u32 w1 = lds_u32(f.col | (f1 & 0x1C00u));
+    const u32 w2 = lds_u32(f.col | (rec.y & 0x1C00u));
+    const u32 w3 = lds_u32(f.col | (f3 & 0x1C00u));
+    u32 idx = (__funnelshift_r(w0, w0, rec.x) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
+    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, rec.y) & ~0xCu);
+    idx = (idx & 0xEu) | (__funnelshift_r(w3, w3, f3) & ~0xEu);
+    const u32 v = __funnelshift_r(rec.z, 0u, idx);
+    const u32 wa_addr = f.col | ((i & ~31u) << 5);
+    const u32 m = __funnelshift_l(0u, 1u, i);
+    old = lds_u32(wa_addr);
+    nw = on ? (old & ~m) | (__funnelshift_l(0u, v, i) & m) : old;
+    sts_u32(wa_addr, nw);
+}
+
 static DrawView make_draws(const PbnDraws *d) {
     DrawView v;
     v.mode = d->mode; v.epoch = d->epoch;
@@ -612,12 +644,15 @@ struct VecView {
     u32 *final_obs, *target_state;
     DrawView rdv;
     CurView cur;
+    double *ep_return_f64, *return_sum_f64;  // self-triggering envs: float64 discounted returns (per env; sum over finished episodes)
 };
 template <int MODE>
 __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev, const VecView &vx, unsigned long long *s_stats,
                                            u32 *state, int *n_steps, int *target_att, u32 *obs_state, long long B,
-                                           long long e, long long env0, int rew, int tm, int tr, int in) {
-    const long long ret = vx.ep_return[e] + rew;
+                                           long long e, long long env0, int rew, int tm, int tr, int in, double rew_f64 = 0.0) {
+    const bool f64 = vx.ep_return_f64 != nullptr;  // self-triggering envs keep float64 returns (self_triggering.py:76,178)
+    const long long ret = f64 ? 0 : vx.ep_return[e] + rew;
+    const double ret_d = f64 ? vx.ep_return_f64[e] + rew_f64 : 0.0;
     const int len = vx.ep_len[e] + 1;
     atomicAdd(&s_stats[5], 1ULL);
     if (tm) atomicAdd(&s_stats[3], 1ULL);
@@ -626,9 +661,12 @@ __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev,
         for (int w = 0; w < nv.w32; w++) vx.final_obs[(long long)w * B + e] = obs_state[(long long)w * B + e];
     if (tm | tr) {
         atomicAdd(&s_stats[0], 1ULL);
-        atomicAdd(&s_stats[1], (unsigned long long)ret);  // two's complement: sums of negative returns wrap correctly
+        if (f64) { atomicAdd(vx.return_sum_f64, ret_d); vx.ep_return_f64[e] = 0.0; }
+        else {
+            atomicAdd(&s_stats[1], (unsigned long long)ret);  // two's complement: sums of negative returns wrap correctly
+            vx.ep_return[e] = 0;
+        }
         atomicAdd(&s_stats[2], (unsigned long long)len);
-        vx.ep_return[e] = 0;
         vx.ep_len[e] = 0;
         if (vx.cur.prob && ev.kind == PBN_ENV_MULTI && ev.n_att >= 2)  // env.rework_probas(episode_len), then the reset draws from it
             rework_probas_dev(vx.cur.prob + e * ev.n_att, ev.n_att, vx.cur.pair[2 * e], vx.cur.pair[2 * e + 1], len);
@@ -637,7 +675,8 @@ __device__ __forceinline__ void vec_finish(const NetView &nv, const EnvView &ev,
             for (int w = 0; w < nv.w32; w++) obs_state[(long long)w * B + e] = state[(long long)w * B + e];  // reset envs observe their new state
         }
     } else {
-        vx.ep_return[e] = ret;
+        if (f64) vx.ep_return_f64[e] = ret_d;
+        else vx.ep_return[e] = ret;
         vx.ep_len[e] = len;
     }
 }
@@ -795,6 +834,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     d.init(dv, e, env0 + e);
     const int *act = actions + e * K;
     int rew = 0, tm = 0, tr = 0, in = 0, bad = 0;
+    double rew_d = 0.0;
     switch (ev.kind) {
     case PBN_ENV_PBN: {  // pbn_env.py:141-154, reward :171-183
         int a = act[0];
@@ -879,6 +919,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
         }
         in = i;
         rew = (int)total;
+        rew_d = total;
         if (rew_f64) rew_f64[e] = total;
     } break;
     default: break;
@@ -891,7 +932,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     if (inner_steps) inner_steps[e] = in;
     if (bad && vx.enabled) atomicAdd(&s_stats[6], 1ULL);  // env.steps whose intervention was out of range (ignored)
     d.done(dv, e);
-    if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, nullptr, obs_state, B, e, env0, rew, tm, tr, in);
+    if (vx.enabled) vec_finish<MODE>(nv, ev, vx, s_stats, state, n_steps, nullptr, obs_state, B, e, env0, rew, tm, tr, in, rew_d);
     }
     vec_flush_stats(vx, s_stats);
 }
@@ -1193,7 +1234,11 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
 // stream (one per two updates) is computed by all lanes at once, nobody pulls work, nothing diverges but the predicate "still
 // running".  Most envs reach an attractor within a few updates and are finished here (coalesced result stores after the loop);
 // the rest are parked for the resume pass (k_env_step_att, groups of lanes).  Same words, same result as any other split.
-template <int TQ>
+// FAST (networks with the 16-byte fast-path records, at most 8 state words, at most two attractor cubes or one state word):
+// the update of the asynchronous rollout kernel (ssd_fast_update: one LOP3 per gather address, rotate-merge LUT index) and
+// an INCREMENTAL attractor test — a mismatch count per cube that moves by -1, 0 or +1 with the one bit an update writes,
+// instead of comparing every state word with every cube after every update.
+template <int TQ, bool FAST>
 __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                               int *target_att, const int *actions, int K, u32 *obs_state,
                                                               int *reward, unsigned char *terminated, unsigned char *truncated,
@@ -1201,11 +1246,13 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
     resolve_epoch(dv);
     resolve_epoch(vx.rdv);
     unsigned char *blob = smem_raw;
-    unsigned char *img = smem_raw + nv.blob_bytes;
-    u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    const int bb = FAST ? nv.blob_fast_bytes : nv.blob_bytes;
+    unsigned char *img = smem_raw + bb;
     const int w32 = nv.w32;
+    u32 *sst = reinterpret_cast<u32 *>(img + ev.img_bytes);
+    if (FAST) sst = align_cols(sst, w32);
     __shared__ unsigned long long s_stats[8];
-    stage(blob, nv.blob, nv.blob_bytes);
+    stage(blob, nv.blob, bb);
     stage(img, ev.img, ev.img_bytes);
     if (threadIdx.x < 8) s_stats[threadIdx.x] = 0;
     const int *att_off = reinterpret_cast<const int *>(img);
@@ -1226,17 +1273,58 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
     u32 x0 = 0, x1 = 0, x2 = 0, x3 = 0;
     int in = 0;
     bool run = valid;
+    // FAST: loop invariants of the update, and the mismatch counts of this env's state against (up to) two cubes
+    SsdFast f;
+    const int n_cubes = ev.n_att > 0 ? att_off[ev.n_att] : 0;
+    const bool inc = FAST && w32 > 1 && n_cubes >= 1 && n_cubes <= 2;  // one-word states are tested directly: two instructions per cube
+    int mm0 = 1, mm1 = 1;
+    bool hit_s0 = false;  // MULTI: the observation captured before the first update, which is what its first test looks at
+    if constexpr (FAST) {
+        f.col = keep(smem_addr(st.s));
+        f.thr = keep(smem_addr(blob + nv.off_thr));
+        f.rec = keep(smem_addr(blob + nv.off_rec16));
+        f.thr_stride = keep((u32)nv.tsq_stride * 16u);
+        f.rec_stride = keep((u32)nv.fmax * 16u);
+        f.n = keep((u32)nv.n);
+        if (inc && valid) {
+            mm0 = mm1 = 0;
+            for (int w = 0; w < w32; w++) {
+                const u32 sw = st.word(w);
+                mm0 += __popc((sw ^ cubes[2 * w + 1]) & cubes[2 * w]);
+                if (n_cubes > 1) mm1 += __popc((sw ^ cubes[2 * (w32 + w) + 1]) & cubes[2 * (w32 + w)]);
+            }
+            if (n_cubes < 2) mm1 = 1;
+            hit_s0 = mm0 == 0 || mm1 == 0;
+        }
+    }
     for (int t = 0;; t++) {  // t updates made so far by every running env
         if (t > 0 && run) {
             // while not is_attracting_state(...): graph.step()  (pbn_target.py:270-271, pbn_target_multi.py:135-146; MULTI's
             // first test looks at the observation captured before the first update)
-            const bool done = (!multi && ev.force) || in >= ev.max_inner || is_attracting_flat(ev, att_off, cubes, (multi && in == 1) ? ob : st, w32);
+            bool hit;
+            if (inc) hit = (multi && in == 1) ? hit_s0 : (mm0 == 0 || mm1 == 0);
+            else hit = is_attracting_flat(ev, att_off, cubes, (multi && in == 1) ? ob : st, w32);
+            const bool done = (!multi && ev.force) || in >= ev.max_inner || hit || ev.n_att == 0;
             run = !done;
         }
         if (t == pl.budget || !__any_sync(0xFFFFFFFFu, run)) break;
         if ((t & 1) == 0) philox4x32_10_rk((u32)(t >> 1), dv.epoch, c2, c3, dv, x0, x1, x2, x3);
-        if (run) {
-            micro_step_words<PBN_NET_PRED, TQ>(nv, blob, st, (t & 1) ? x2 : x0, (t & 1) ? x3 : x1, dummy);
+        const u32 wa = (t & 1) ? x2 : x0, wb = (t & 1) ? x3 : x1;
+        if constexpr (FAST) {
+            u32 i, old, nw;
+            fast_update_io<TQ>(f, wa, wb, run, i, old, nw);
+            if (inc) {
+                const u32 flip = old ^ nw;  // the written bit, if it changed
+                const uint2 c0 = reinterpret_cast<const uint2 *>(cubes)[i >> 5];
+                mm0 += (flip & c0.x) ? (((nw ^ c0.y) & flip) ? 1 : -1) : 0;
+                if (n_cubes > 1) {
+                    const uint2 c1 = reinterpret_cast<const uint2 *>(cubes)[w32 + (i >> 5)];
+                    mm1 += (flip & c1.x) ? (((nw ^ c1.y) & flip) ? 1 : -1) : 0;
+                }
+            }
+            in += run ? 1 : 0;
+        } else if (run) {
+            micro_step_words<PBN_NET_PRED, TQ>(nv, blob, st, wa, wb, dummy);
             in++;
         }
     }
@@ -1842,6 +1930,7 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
                          uint8_t *truncated, int32_t *inner_steps, int64_t B, int64_t env0, const PbnDraws *draws,
                          const PbnVecState *vec, void *stream, double *reward_f64 = nullptr, const PbnStepPlan *plan = nullptr) {
     if (!env || !state || !actions || !reward || !terminated || !truncated || B < 0 || K < 1) return fail(PBN_ERR_ARG, "bad argument");
+    if (!reward_f64 && vec && vec->reward_f64) reward_f64 = vec->reward_f64;
     {
         const int kd = env->v.kind;
         if ((kd == PBN_ENV_PBN_ST || kd == PBN_ENV_PBCN_ST) && !reward_f64)
@@ -1861,7 +1950,10 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
     VecView vx;
     memset(&vx, 0, sizeof vx);
     if (vec) {
-        if (!vec->ep_return || !vec->ep_len || !vec->stats || !obs_state) return fail(PBN_ERR_ARG, "vector step needs ep_return, ep_len, stats and obs_state");
+        const bool st_kind = ev.kind == PBN_ENV_PBN_ST || ev.kind == PBN_ENV_PBCN_ST;
+        if (st_kind && (!vec->ep_return_f64 || !vec->return_sum_f64))
+            return fail(PBN_ERR_ARG, "the vector step of a self-triggering env needs ep_return_f64 and return_sum_f64");
+        if ((!st_kind && !vec->ep_return) || !vec->ep_len || !vec->stats || !obs_state) return fail(PBN_ERR_ARG, "vector step needs ep_return, ep_len, stats and obs_state");
         if (vec->autoreset) {
             if (int rc = check_draws(&vec->reset_draws)) return rc;
             const bool tgt = ev.kind == PBN_ENV_TARGET || ev.kind == PBN_ENV_MULTI;
@@ -1873,6 +1965,7 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         vx.enabled = 1; vx.autoreset = vec->autoreset;
         vx.ep_return = (long long *)vec->ep_return; vx.ep_len = vec->ep_len; vx.stats = (unsigned long long *)vec->stats;
         vx.final_obs = vec->final_obs; vx.target_state = vec->target_state;
+        if (st_kind) { vx.ep_return_f64 = vec->ep_return_f64; vx.return_sum_f64 = vec->return_sum_f64; }
         if (vec->probabilities) {
             if (ev.kind != PBN_ENV_MULTI || !vec->pair_ids || ev.n_att < 2 || ev.n_att > 64)
                 return fail(PBN_ERR_ARG, "a probability table needs a MULTI env with 2..64 attractors and pair_ids");
@@ -1907,11 +2000,17 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
     const int coop_on = att && smem + coop_bytes <= 200 * 1024 && !(plan && !pl.resume && pl.budget > 0);
     if (coop_on) smem += coop_bytes;
     if (plan && !pl.resume && pl.budget > 0 && nv.kind == PBN_NET_PRED) {  // lockstep first pass (Philox: checked above)
-#define FIRST(TQ)                                                                                                 \
-        if (int rc = set_smem(k_env_step_first<TQ>, smem)) return rc;                                             \
-        k_env_step_first<TQ><<<grid, block, smem, s>>>(nv, ev, dv, state, n_steps, const_cast<int32_t *>(target_att), actions, K, \
+        const bool fast = nv.off_rec16 != 0 && nv.w32 <= 8 && (nv.ts == 4 || nv.ts == 16);
+        const size_t smem_f = (size_t)nv.blob_fast_bytes + ev.img_bytes + col_align_bytes(nv.w32) + (size_t)2 * nv.w32 * block * 4;
+#define FIRST(TQ, FAST, SM)                                                                                       \
+        if (int rc = set_smem(k_env_step_first<TQ, FAST>, SM)) return rc;                                         \
+        k_env_step_first<TQ, FAST><<<grid, block, SM, s>>>(nv, ev, dv, state, n_steps, const_cast<int32_t *>(target_att), actions, K, \
                                                       obs_state, reward, terminated, truncated, inner_steps, B, env0, pl, vx)
-        if (nv.ts == 4) { FIRST(1); } else if (nv.ts == 16) { FIRST(4); } else { FIRST(0); }
+        if (fast && nv.ts == 4) { FIRST(1, true, smem_f); }
+        else if (fast) { FIRST(4, true, smem_f); }
+        else if (nv.ts == 4) { FIRST(1, false, smem); }
+        else if (nv.ts == 16) { FIRST(4, false, smem); }
+        else { FIRST(0, false, smem); }
 #undef FIRST
         CK(cudaGetLastError());
         return PBN_OK;

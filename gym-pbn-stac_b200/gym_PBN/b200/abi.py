@@ -45,7 +45,8 @@ class PbnFitDesc(C.Structure):
 class PbnVecState(C.Structure):
     _fields_ = [("ep_return", C.c_void_p), ("ep_len", C.c_void_p), ("stats", C.c_void_p), ("final_obs", C.c_void_p),
                 ("target_state", C.c_void_p), ("autoreset", C.c_int32), ("reset_draws", PbnDraws),
-                ("probabilities", C.c_void_p), ("pair_ids", C.c_void_p), ("sample_pair", C.c_int32)]
+                ("probabilities", C.c_void_p), ("pair_ids", C.c_void_p), ("sample_pair", C.c_int32),
+                ("reward_f64", C.c_void_p), ("ep_return_f64", C.c_void_p), ("return_sum_f64", C.c_void_p)]
 
 
 class PbnStepPlan(C.Structure):

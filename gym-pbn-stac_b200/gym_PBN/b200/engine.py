@@ -164,8 +164,14 @@ class Simulator:
         # plan_budgets[0] updates per env (every lane owns an env; most envs finish there), resume passes with the further
         # budgets (the envs still outside every attractor, run by groups of lanes and spread over the whole GPU: each pass
         # sheds the envs that finish, so the next one runs fewer envs per warp in wider, faster groups) and a last pass to the
-        # end; () = one launch does everything
-        self.plan_budgets = (32, 256)
+        # end; () = one launch does everything.  "auto" (default) sizes the first pass to the workload: (b, 8b) with b the
+        # smallest of 32, 64, 128, 256 within which at least half of the envs finish their env.step — 32 when most envs need a
+        # few updates (Bittner-28: median 6, however heavy the tail), 256 when they need hundreds (Bittner-200 on its real
+        # attractor; the lockstep pass moves 2x the updates per instruction the lane groups do).  The counts come from the
+        # previous steps' update counts, read back asynchronously every 16th step (no synchronisation; every plan gives the
+        # same results)
+        self.plan_budgets = "auto"
+        self._auto = {"b": 32, "steps": 0, "host": None, "event": None}
         self.running = None   # bool [B]: envs whose env.step is unfinished (budgeted stepping)
         self._work = None     # int32 [2 * (B + 4)]: the two parking lists
         self._plan_phase = 0
@@ -239,10 +245,38 @@ class Simulator:
         return (replay is None and env.kind in (abi.ENV_TARGET, abi.ENV_MULTI) and env.n_att > 0 and not env.force
                 and len(self._passes(env)) > 1)
 
+    def _auto_poll(self):
+        a = self._auto
+        if a["event"] is None or torch.cuda.is_current_stream_capturing():
+            return
+        if a["event"].query():  # a finished read-back: update the first-pass budget
+            counts = a["host"].tolist()
+            a["b"] = next((b for b, c in zip((32, 64, 128), counts) if 2 * c >= self.B), 256)
+            a["event"] = None
+
+    def _auto_sample(self):
+        """Every 16th planned step: sum of the step's update counts -> pinned host memory, no synchronisation."""
+        a = self._auto
+        if not isinstance(self.plan_budgets, str):
+            return
+        a["steps"] += 1
+        if a["steps"] % 16 != 1 or a["event"] is not None or torch.cuda.is_current_stream_capturing():
+            return
+        if a["host"] is None:
+            a["host"] = torch.zeros(3, dtype=torch.int64).pin_memory()
+            a["thr"] = torch.tensor([[32], [64], [128]], dtype=torch.int32, device=self.device)
+        a["host"].copy_((self.inner.unsqueeze(0) <= a["thr"]).sum(1), non_blocking=True)  # envs done within 32 / 64 / 128 updates
+        a["event"] = torch.cuda.Event()
+        a["event"].record()
+
     def _passes(self, env):
         """Budgets of the passes of one full env.step: plan_budgets as far as the cap can exceed them, then 0 (to the end)."""
         out, spent = [], 0
-        for b in self.plan_budgets:
+        budgets = self.plan_budgets
+        if isinstance(budgets, str):
+            self._auto_poll()
+            budgets = (self._auto["b"], 8 * self._auto["b"])
+        for b in budgets:
             b = max(int(b), 2)
             if spent + b >= env.max_inner:
                 break
@@ -266,6 +300,7 @@ class Simulator:
             else:
                 for k, b in enumerate(self._passes(env)):
                     self._plan_call(env, actions, d, b, int(k > 0))
+                self._auto_sample()
             return
         if env.kind in (abi.ENV_PBN_ST, abi.ENV_PBCN_ST):  # discounted float64 reward (self.reward_f64), interval in self.inner
             if getattr(self, "reward_f64", None) is None:
@@ -291,19 +326,24 @@ class Simulator:
         self._plan_call(env, self._plan_actions, self._plan_draws, budget, 1)
 
     def vec_step(self, env: EnvImage, actions, ep_return, ep_len, stats, final_obs=None, autoreset=True, curriculum=None,
-                 epoch_dev=None, epoch_base=None):
+                 epoch_dev=None, epoch_base=None, return_sum_f64=None):
         """Fused vector-env step (one launch): env.step for every env + episode bookkeeping + statistics + reset of the envs
         that finished.  Consumes two epochs (step, reset) exactly like env_step followed by a masked env_reset."""
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, dtype=torch.int32).contiguous()
         K = actions.numel() // self.B
         key = (env.handle.value, ep_return.data_ptr(), final_obs.data_ptr() if final_obs is not None else 0, bool(autoreset),
-               tuple(self.plan_budgets), curriculum[0].data_ptr() if curriculum else 0)
+               tuple(self._passes(env)), curriculum[0].data_ptr() if curriculum else 0)
         c = self._vec_cache
         if c is None or c["key"] != key:  # the buffers never move: build the argument block once
             d, rd = abi.PbnDraws(mode=abi.DRAW_PHILOX), abi.PbnDraws(mode=abi.DRAW_PHILOX)
             v = abi.PbnVecState(ep_return=_ptr(ep_return), ep_len=_ptr(ep_len), stats=_ptr(stats), final_obs=_ptr(final_obs),
                                 target_state=_ptr(self.target_state), autoreset=int(bool(autoreset)))
+            if env.kind in (abi.ENV_PBN_ST, abi.ENV_PBCN_ST):  # float64 reward / return (ep_return is a float64 tensor here)
+                if getattr(self, "reward_f64", None) is None:
+                    self.reward_f64 = torch.zeros(self.B, dtype=torch.float64, device=self.device)
+                v.ep_return, v.ep_return_f64 = None, _ptr(ep_return)
+                v.reward_f64, v.return_sum_f64 = _ptr(self.reward_f64), _ptr(return_sum_f64)
             if curriculum:  # (probabilities float64 [B][A], pair_ids int32 [B][2], sample_pair)
                 v.probabilities, v.pair_ids, v.sample_pair = _ptr(curriculum[0]), _ptr(curriculum[1]), int(bool(curriculum[2]))
             head = (env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att))
@@ -333,6 +373,7 @@ class Simulator:
                     if rc:
                         abi.check(rc)
                     self.launches += 1
+                self._auto_sample()
                 return
             rc = c["fn"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(v), self.B, self.env0, C.byref(d), stream)
             if rc:

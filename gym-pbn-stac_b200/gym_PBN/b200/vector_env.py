@@ -97,7 +97,7 @@ class PBNVectorEnv:
         self.stats = pdist.EpisodeStats(self.device)
         self.ep_return = torch.zeros(self.num_envs, dtype=torch.float64 if self.family == "st" else torch.int64,
                                      device=self.device)
-        self.return_sum_f64 = torch.zeros((), dtype=torch.float64, device=self.device)  # "st": stats.v[1] stays 0
+        self._return_sum = torch.zeros(1, dtype=torch.float64, device=self.device)  # "st": stats.v[1] stays 0
         self.ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self.final_obs = torch.zeros_like(self.sim.state)
         self._needs_reset = True
@@ -188,30 +188,21 @@ class PBNVectorEnv:
 
     def _step_self_triggering(self, actions):
         """Macro step of every env (actions int32 [B][2] = (primitive, prob) for the PBN variant, [B][1+M] = (prob, control
-        bits) for the PBCN variant); rewards are float64 [B], info["interval"] the primitive steps each env took.  Same draw
+        bits) for the PBCN variant); rewards are float64 [B], info["interval"] the primitive steps each env took.  ONE launch
+        (pbn_vec_step): macro step + float64 return bookkeeping + statistics + reset of the finished envs, the same draw
         consumption as Simulator.env_step followed by a masked Simulator.env_reset (one epoch each)."""
         sim = self.sim
-        sim.env_step(self.image, actions)
-        reward, term, trunc = sim.reward_f64, sim.terminated, sim.truncated
-        done = term | trunc
-        self.ep_return += reward
-        self.ep_len += 1
-        v = self.stats.v
-        n_done = done.sum()
-        v[0] += n_done
-        v[2] += (self.ep_len * done).sum()
-        v[3] += term.sum()
-        v[5] += self.num_envs
-        self.return_sum_f64 += (self.ep_return * done).sum()
-        self.final_obs.copy_(sim.state)
-        self.ep_return.masked_fill_(done, 0.0)
-        self.ep_len.masked_fill_(done, 0)
-        if self.autoreset:
-            sim.env_reset(self.image, mask=done)
-        else:
-            sim.epoch += 1  # keep the epoch schedule independent of the flag
-        info = {"interval": sim.inner, "inner_steps": sim.inner, "packed_obs": sim.state, "final_obs_packed": self.final_obs}
-        return self._obs(sim.state), reward, term, trunc, info
+        if actions.dtype != torch.int32 or actions.device != self.device:
+            actions = actions.to(self.device, dtype=torch.int32)
+        sim.vec_step(self.image, actions.reshape(self.num_envs, self.action_width).contiguous(), self.ep_return, self.ep_len,
+                     self.stats.v, final_obs=self.final_obs, autoreset=self.autoreset, return_sum_f64=self._return_sum)
+        info = {"interval": sim.inner, "inner_steps": sim.inner, "packed_obs": sim.obs_state, "final_obs_packed": self.final_obs}
+        return self._obs(sim.obs_state), sim.reward_f64, sim.terminated, sim.truncated, info
+
+    @property
+    def return_sum_f64(self):
+        """Self-triggering envs: sum of the float64 returns of all finished episodes (device scalar)."""
+        return self._return_sum[0]
 
     def step_host(self, actions_host):
         """Host in / host out convenience (pinned staging): NumPy actions -> NumPy (obs, reward, terminated, truncated)."""

@@ -162,6 +162,13 @@ typedef struct {
     double *probabilities;  /* [B][n_att], NULL = no curriculum */
     int32_t *pair_ids;      /* [B][2] */
     int32_t sample_pair;
+    /* self-triggering envs (PBN_ENV_PBN_ST / PBN_ENV_PBCN_ST; self_triggering.py:56-93,146-197): the macro step's discounted
+       float64 reward, the running float64 episode return (instead of ep_return) and the sum of finished episodes' returns
+       (instead of stats[1]); with these pbn_vec_step serves them like the other kinds: macro step + bookkeeping + reset in
+       one launch */
+    double *reward_f64;      /* [B] */
+    double *ep_return_f64;   /* [B] */
+    double *return_sum_f64;  /* [1] */
 } PbnVecState;
 int pbn_vec_step(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int32_t *target_att, const int32_t *actions,
                  int32_t K, uint32_t *obs_state, int32_t *reward, uint8_t *terminated, uint8_t *truncated,

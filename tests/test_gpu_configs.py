@@ -180,7 +180,7 @@ def test_step_plan_matches_single_launch(eng):
     """The two-pass default of Simulator.env_step against the one-launch kernel (plan_budgets = ()), cap hits included."""
     B, seed = 20000, 5
     res = []
-    for p1 in ((32, 256), (), (4,), (2, 2, 2, 100)):
+    for p1 in ((32, 256), (), (4,), (2, 2, 2, 100), "auto"):
         net, onet, env, oenv, sim, _, acts = _target_case(eng, "28_15_median", "target", 1, B, seed, max_inner=300, care=28,
                                                           full_care=True)
         sim.plan_budgets = p1

@@ -7,13 +7,21 @@ sys.path.insert(0, str(ROOT / "gym-pbn-stac_b200"))
 from gym_PBN.b200 import abi, compiler, engine  # noqa: E402
 from gym_PBN.b200 import attractors as att_tools  # noqa: E402
 
-net = engine.Network(compiler.load_bittner("28_15_median"))
-atts = att_tools.exact_attractor_cubes(net)
-env = engine.EnvImage(net, abi.ENV_TARGET, attractors=atts, horizon=100, max_inner=4096)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 plan = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [32, 256, 0]
+which = sys.argv[3] if len(sys.argv) > 3 else "c2"
 torch.manual_seed(0)
-acts = torch.randint(0, 29, (B, 1), dtype=torch.int32, device="cuda")
+if which == "c2":
+    net = engine.Network(compiler.load_bittner("28_15_median"))
+    atts = att_tools.exact_attractor_cubes(net)
+    env = engine.EnvImage(net, abi.ENV_TARGET, attractors=atts, horizon=100, max_inner=4096)
+    acts = torch.randint(0, 29, (B, 1), dtype=torch.int32, device="cuda")
+else:  # config 4: Bittner-200 multi on its verified attractor
+    import json
+    net = engine.Network(compiler.load_bittner("200_5_kmeans"))
+    atts = [[tuple(c) for c in a] for a in json.loads((ROOT / "tests" / "golden" / "b200_verified_attractors.json").read_text())]
+    env = engine.EnvImage(net, abi.ENV_MULTI, attractors=atts, horizon=100, max_inner=4096, dedup=True)
+    acts = torch.randint(0, net.n + 1, (B, 3), dtype=torch.int32, device="cuda")
 sim = engine.Simulator(net, B, seed=1)
 sim.env_reset(env)
 for it in range(4):
