@@ -1021,7 +1021,9 @@ struct PlanView {
     int *list_in, *list_out;
 };
 
-template <int NET, int MODE, int TQ>
+// W1: one-word networks (N <= 32) — the group runner keeps the state in a register; a separate instantiation, because both
+// runners inlined in one kernel made it 120 KB of SASS and instruction fetch its top stall (ncu: no_inst 21 %)
+template <int NET, int MODE, int TQ, bool W1>
 __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                             const int *target_att, const int *actions, int K, u32 *obs_state,
                                                             int *reward, unsigned char *terminated, unsigned char *truncated,
@@ -1208,8 +1210,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                 // block's queue lasts, start the next env), the other envs come back here — in wider groups once the queue
                 // is empty, which is why the first stop ends the call then
                 const int exit_at = drained ? 1 : PBN_COOP_EXIT_AT;
-                const int fin = w32 == 1 ? coop_steps<TQ, true>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at)
-                                         : coop_steps<TQ, false>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at);
+                const int fin = coop_steps<TQ, W1>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at);
                 __syncwarp();
                 for (int r = 0; r < nl; r++) {          // hand each group's count back to the lane that owns the env
                     const int v = __shfl_sync(0xFFFFFFFFu, fin, r * g);
@@ -2015,24 +2016,31 @@ static int env_step_impl(const PbnEnv *env, uint32_t *state, int32_t *n_steps, c
         CK(cudaGetLastError());
         return PBN_OK;
     }
+#define ATT_LAUNCH(NK, MD, TQ, W1)                                                                                \
+        if (int rc = set_smem(k_env_step_att<NK, MD, TQ, W1>, smem)) return rc;                                   \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD, TQ, W1>, block, smem));     \
+        att_grid();                                                                                               \
+        k_env_step_att<NK, MD, TQ, W1><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
+                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, coop_on, grp_mode, pl, vx)
 #define CALL(NK, MD, TQ)                                                                                          \
     if (att) {                                                                                                    \
-        if (int rc = set_smem(k_env_step_att<NK, MD, TQ>, smem)) return rc;                                       \
         /* persistent grid: as many blocks as stay resident, each owning a contiguous range of envs */            \
         int dev = 0, sms = 0, bps = 0;                                                                            \
         CK(cudaGetDevice(&dev));                                                                                  \
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                    \
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_env_step_att<NK, MD, TQ>, block, smem));         \
-        long long pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                   \
+        long long pgrid = 0, per_block = 0;                                                                       \
         /* group mode pays when env.steps can be long; under a small cap a lane per env (4x the envs in flight) is faster */ \
         const int grp_mode = coop_on && NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && ev.n_att > 0 && !ev.force && \
                              (ev.max_inner > 64 || pl.resume);                                                    \
-        const long long cap_grid = grp_mode ? (B + PBN_BLOCK / 4 - 1) / (PBN_BLOCK / 4) : (long long)grid;        \
-        if (pgrid > cap_grid) pgrid = cap_grid;  /* (a resume pass learns its env count on the device) */         \
-        const long long per_block = (B + pgrid - 1) / pgrid;                                                      \
-        pgrid = (B + per_block - 1) / per_block;                                                                  \
-        k_env_step_att<NK, MD, TQ><<<(unsigned)pgrid, block, smem, s>>>(nv, ev, dv, state, n_steps, target_att, actions, K, obs_state, \
-                                                         reward, terminated, truncated, inner_steps, B, env0, per_block, coop_on, grp_mode, pl, vx); \
+        auto att_grid = [&]() {                                                                                   \
+            pgrid = (long long)sms * (bps > 0 ? bps : 1);                                                         \
+            const long long cap_grid = grp_mode ? (B + PBN_BLOCK / 4 - 1) / (PBN_BLOCK / 4) : (long long)grid;    \
+            if (pgrid > cap_grid) pgrid = cap_grid;  /* (a resume pass learns its env count on the device) */     \
+            per_block = (B + pgrid - 1) / pgrid;                                                                  \
+            pgrid = (B + per_block - 1) / per_block;                                                              \
+        };                                                                                                        \
+        if (NK == PBN_NET_PRED && MD == PBN_DRAW_PHILOX && nv.w32 == 1) { ATT_LAUNCH(NK, MD, TQ, true); }         \
+        else { ATT_LAUNCH(NK, MD, TQ, false); }                                                                   \
     } else {                                                                                                      \
         const size_t smem1 = (size_t)nv.blob_bytes + ev.img_bytes + (size_t)nv.w32 * block * 4; /* one column per env */ \
         if (int rc = set_smem(k_env_step<NK, MD>, smem1)) return rc;                                              \

@@ -274,8 +274,15 @@ class Simulator:
         out, spent = [], 0
         budgets = self.plan_budgets
         if isinstance(budgets, str):
-            self._auto_poll()
-            budgets = (self._auto["b"], 8 * self._auto["b"])
+            # a lockstep round costs ~1 us whatever the batch (a lane's update is a ~2000-cycle chain; the pass is efficient
+            # only when the GPU is full of lanes), a group's update 0.03-0.07 us: small batches skip the lockstep pass (one
+            # launch, group mode), medium ones keep it short
+            if self.B <= 8192:
+                budgets = ()
+            else:
+                self._auto_poll()
+                b = self._auto["b"] if self.B >= 65536 else 32
+                budgets = (b, 8 * b)
         for b in budgets:
             b = max(int(b), 2)
             if spent + b >= env.max_inner:
