@@ -328,6 +328,7 @@ struct SsdFast {
     u32 thr_stride, rec_stride;  // bytes per node
     u32 shist;      // shared address of the block histogram
     u32 n, W;
+    u32 Wu;         // W again, not pinned in a vector register
     u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
     float inv, gdelta;  // gdelta: 0.5 - margin of the gap shortcut
 };
@@ -343,9 +344,14 @@ __device__ __forceinline__ u32 count_le_x16(const uint4 t, u32 r) {
     return j8;
 }
 
-// one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312)
+// one asynchronous update of a predictor network from two words of the update stream (bittner/base.py:89-119,306-312), in two
+// halves: the DRAW half (node, predictor pick, the predictor's record) depends only on the stream and can be issued ahead of
+// whatever still changes the state; the STATE half gathers the four input bits, looks the LUT bit up and writes it
+struct FastDraw {
+    u32 i, rx, ry, rz;
+};
 template <int TQ>
-__device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
+__device__ __forceinline__ FastDraw ssd_fast_draw(const SsdFast &f, u32 wa, u32 wb) {
     const u32 i = __umulhi(wa, f.n);  // Graph.step picks i in [0, N)
     const u32 r = wb >> 1;
     u32 j16;  // 16 * (index of the selected predictor)
@@ -358,20 +364,27 @@ __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb
         j16 = 64u * q + count_le_x16(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
     }
     const uint4 rec = ldc_v4(f.rec + i * f.rec_stride + j16);
-    const u32 f1 = rec.x >> 16, f3 = rec.y >> 16;
+    return FastDraw{i, rec.x, rec.y, rec.z};
+}
+__device__ __forceinline__ void ssd_fast_apply_update(const SsdFast &f, const FastDraw &d) {
+    const u32 f1 = d.rx >> 16, f3 = d.ry >> 16;
     // columns are aligned (align_cols): column address | word offset; a rotate brings input j's bit to position 3 - j
-    const u32 w0 = lds_u32(f.col | (rec.x & 0x1C00u));
+    const u32 w0 = lds_u32(f.col | (d.rx & 0x1C00u));
     const u32 w1 = lds_u32(f.col | (f1 & 0x1C00u));
-    const u32 w2 = lds_u32(f.col | (rec.y & 0x1C00u));
+    const u32 w2 = lds_u32(f.col | (d.ry & 0x1C00u));
     const u32 w3 = lds_u32(f.col | (f3 & 0x1C00u));
-    u32 idx = (__funnelshift_r(w0, w0, rec.x) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
-    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, rec.y) & ~0xCu);
+    u32 idx = (__funnelshift_r(w0, w0, d.rx) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
+    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, d.ry) & ~0xCu);
     idx = (idx & 0xEu) | (__funnelshift_r(w3, w3, f3) & ~0xEu);  // bits 3..0: LUT index; above: garbage (shifts wrap, LUT doubled)
-    const u32 v = __funnelshift_r(rec.z, 0u, idx);
-    const u32 wa_addr = f.col | ((i & ~31u) << 5);
-    const u32 m = __funnelshift_l(0u, 1u, i);  // 1 << (i & 31)
+    const u32 v = __funnelshift_r(d.rz, 0u, idx);
+    const u32 wa_addr = f.col | ((d.i & ~31u) << 5);
+    const u32 m = __funnelshift_l(0u, 1u, d.i);  // 1 << (i & 31)
     const u32 old = lds_u32(wa_addr);
-    sts_u32(wa_addr, (old & ~m) | (__funnelshift_l(0u, v, i) & m));  // bit i <- LUT bit idx
+    sts_u32(wa_addr, (old & ~m) | (__funnelshift_l(0u, v, d.i) & m));  // bit i <- LUT bit idx
+}
+template <int TQ>
+__device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb) {
+    ssd_fast_apply_update(f, ssd_fast_draw<TQ>(f, wa, wb));
 }
 
 #include "pbn_coop.cuh"
@@ -1423,14 +1436,17 @@ __device__ __forceinline__ u32 warp_scan_add(u32 v) {
 
 // The SSD iteration loop of one warp.  FULL = every lane owns a chain (all warps but possibly the last of the job).
 // PHILOX perturbation: ONE Bernoulli(p) renewal process per group of 32 consecutive chains over the interleaved index
-// c = node*32 + lane (window = 32*n positions per iteration).  Each round every lane draws one geometric gap from its
-// own PERTURBATION stream (block indices from 2^31 on), a warp prefix sum turns the 32 gaps into 32 event positions, and
-// an event inside the current window flips bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law as n
-// independent Bernoulli(p) per chain per iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence.
+// c = node*32 + lane (window = 32*n positions per iteration).  Each ROUND every lane draws TWO geometric gaps from
+// consecutive words of its own PERTURBATION stream (block indices from 2^31 on); the round's 64 events are ordered
+// lane-major (lane l holds events 2l and 2l+1), one warp prefix sum over the lanes' (gap + 1) pairs turns them into 64 event
+// positions, and an event inside the current window flips bit (c>>5) of chain (c&31) with a shared-memory atomic.  Same law
+// as n independent Bernoulli(p) per chain per iteration (eval.py:92-95), ~1 draw per chain per iteration, no divergence,
+// and at p*n = 1 a round (mean span: two windows) is due every second iteration.  A round is drawn only when the previous
+// one lies wholly inside the current window, so two event slots per lane are enough.
 // The UPDATE stream is then consumed at exactly two words per update, so when every iteration is one update (no
 // attractor loop) a Philox block serves two iterations with no buffer bookkeeping (STATIC path below).
 struct SsdPerturb {
-    u32 evp;      // this lane's pending event, relative to the window start (0xFFFFFFFF = none)
+    u32 e0, e1;   // this lane's pending events, relative to the window start (0xFFFFFFFF = none)
     u32 last_p1;  // (position of the last generated event) + 1, relative to the window start
 };
 
@@ -1442,22 +1458,34 @@ __device__ __forceinline__ u32 ssd_gap(u32 word, float inv, float hmd) {
     return gap;
 }
 
+// positions of a round's events from this lane's two gaps
+__device__ __forceinline__ void ssd_round(SsdPerturb &ps, u32 g0, u32 g1) {
+    const u32 incl = warp_scan_add(g0 + g1 + 2u);
+    ps.e1 = ps.last_p1 - 1u + incl;
+    ps.e0 = ps.e1 - 1u - g1;
+    ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.e1, 31) + 1u;
+}
+
 template <bool FULL>
 __device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, char *warp_cols, u32 W, float inv, float hmd, u32 nvalid) {
-    for (;;) {
-        if (ps.evp < W) {
-            const u32 tl = ps.evp & 31u;
-            // word (node>>5) of column tl: byte offset = tl*4 + (node>>5)*1024, node = evp>>5
-            if (FULL || tl < nvalid)
-                atomicXor(reinterpret_cast<u32 *>(warp_cols + tl * 4u + ((ps.evp >> 10) << 10)), 1u << ((ps.evp >> 5) & 31u));
-            ps.evp = 0xFFFFFFFFu;
+    auto apply = [&](u32 &e) {
+        if (e < W) {
+            const u32 tl = e & 31u;
+            // word (node>>5) of column tl: byte offset = tl*4 + (node>>5)*1024, node = e>>5
+            if (FULL || tl < nvalid) atomicXor(reinterpret_cast<u32 *>(warp_cols + tl * 4u + ((e >> 10) << 10)), 1u << ((e >> 5) & 31u));
+            e = 0xFFFFFFFFu;
         }
+    };
+    for (;;) {
+        apply(ps.e0);
+        apply(ps.e1);
         if (ps.last_p1 > W) break;  // the last generated event lies beyond this window
-        const u32 pre = warp_scan_add(1u + ssd_gap(dp.next(), inv, hmd));
-        ps.evp = ps.last_p1 - 1u + pre;
-        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+        const u32 g0 = ssd_gap(dp.next(), inv, hmd);
+        const u32 g1 = ssd_gap(dp.next(), inv, hmd);
+        ssd_round(ps, g0, g1);
     }
-    if (ps.evp != 0xFFFFFFFFu) ps.evp -= W;
+    if (ps.e0 != 0xFFFFFFFFu) ps.e0 -= W;
+    if (ps.e1 != 0xFFFFFFFFu) ps.e1 -= W;
     ps.last_p1 -= W;
     __syncwarp();
 }
@@ -1466,18 +1494,23 @@ __device__ __forceinline__ void ssd_perturb(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX
 // buf[w*32 + tl]) instead of being applied: the windowed loop below draws the masks of several iterations ahead.
 template <bool FULL>
 __device__ __forceinline__ void ssd_perturb_buf(SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, u32 *buf, u32 W, float inv, float hmd, u32 nvalid) {
-    for (;;) {
-        if (ps.evp < W) {
-            const u32 tl = ps.evp & 31u;
-            if (FULL || tl < nvalid) atomicXor(buf + ((ps.evp >> 10) << 5) + tl, 1u << ((ps.evp >> 5) & 31u));
-            ps.evp = 0xFFFFFFFFu;
+    auto apply = [&](u32 &e) {
+        if (e < W) {
+            const u32 tl = e & 31u;
+            if (FULL || tl < nvalid) atomicXor(buf + ((e >> 10) << 5) + tl, 1u << ((e >> 5) & 31u));
+            e = 0xFFFFFFFFu;
         }
+    };
+    for (;;) {
+        apply(ps.e0);
+        apply(ps.e1);
         if (ps.last_p1 > W) break;
-        const u32 pre = warp_scan_add(1u + ssd_gap(dp.next(), inv, hmd));
-        ps.evp = ps.last_p1 - 1u + pre;
-        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+        const u32 g0 = ssd_gap(dp.next(), inv, hmd);
+        const u32 g1 = ssd_gap(dp.next(), inv, hmd);
+        ssd_round(ps, g0, g1);
     }
-    if (ps.evp != 0xFFFFFFFFu) ps.evp -= W;
+    if (ps.e0 != 0xFFFFFFFFu) ps.e0 -= W;
+    if (ps.e1 != 0xFFFFFFFFu) ps.e1 -= W;
     ps.last_p1 -= W;
 }
 
@@ -1495,25 +1528,58 @@ __device__ __forceinline__ void ssd_count(SsdCount &c, const SsdLoopArgs &a, con
     c.run++;
 }
 
-// "No pending event" is any value >= W here: 0xFFFFFFFF is only ever lowered by W per iteration until the next round
-// overwrites it, and a round comes at the latest after 32 capped gaps (< 2^31 positions), so it never reaches the window.
-__device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &ps, Draw<PBN_DRAW_PHILOX> &dp, const DrawView &dv) {
-    for (;;) {
-        // word (node>>5) of column (evp&31): byte offset = (evp&31)*4 + (node>>5)*1024, node = evp>>5; predicated, no branch
-        asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p red.shared.xor.b32 [%2], %3; }"
-                     :: "r"(ps.evp), "r"(f.W), "r"((f.warp_cols | ((ps.evp << 2) & 0x7Cu)) | (ps.evp & 0xFFFFFC00u)),
-                        "r"(1u << ((ps.evp >> 5) & 31u)) : "memory");
-        if (ps.last_p1 > f.W) break;  // otherwise every pending event lay inside this window and has just been applied
-        const u32 word = dp.next_rk(dv);
-        bool ok;
-        u32 gap = geom_gap_approx(word, f.inv, f.gdelta, &ok);
-        if (!ok) gap = geom_gap(word, f.inv);  // within the margin of an integer (or shortcut off): the defining polynomial
-        const u32 pre = warp_scan_add(1u + gap);
-        ps.evp = ps.last_p1 - 1u + pre;
-        ps.last_p1 = __shfl_sync(0xFFFFFFFFu, ps.evp, 31) + 1u;
+// Perturbation state of the static loop: the lane's two event slots, and its perturbation stream held as "next block index +
+// the unused half of the last block" (a round takes two words, so every second round computes a block).
+// "No pending event" is any value >= W here: an applied event is only ever lowered by W per iteration (it wraps to a value
+// above 2^32 - 2^31) until the next round overwrites it, and a round comes at the latest after 64 gaps of at most 2^25.
+struct SsdFastPerturb {
+    u32 e0, e1, last_p1;
+    u32 blk, half, sx, sy;
+};
+
+// flip the bit of an event that lies inside the window: word (node>>5) of column (e&31), byte offset = (e&31)*4 + (node>>5)*1024,
+// node = e>>5; predicated, no branch in the source (ptxas may still branch around the atomic)
+__device__ __forceinline__ void ssd_fast_apply(const SsdFast &f, u32 e) {
+    asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p red.shared.xor.b32 [%2], %3; }"
+                 :: "r"(e), "r"(f.W), "r"((f.warp_cols | ((e << 2) & 0x7Cu)) | (e & 0xFFFFFC00u)),
+                    "r"(1u << ((e >> 5) & 31u)) : "memory");
+}
+
+__device__ __forceinline__ u32 ssd_fast_gap(const SsdFast &f, u32 word, bool &ok) { return geom_gap_approx(word, f.inv, f.gdelta, &ok); }
+
+__device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdFastPerturb &ps, const Draw<PBN_DRAW_PHILOX> &dp, const DrawView &dv) {
+    ssd_fast_apply(f, ps.e0);
+    ssd_fast_apply(f, ps.e1);
+    // last_p1 comes out of a warp reduction: the compiler knows it is the same in every lane and branches on it without
+    // reconvergence code
+    while (ps.last_p1 <= f.Wu) {  // every pending event lay inside this window and has just been applied: the next round
+        u32 wa, wb;
+        if (ps.half == 0u) {  // a round takes two words: every second one computes a block
+            u32 x2, x3;
+            philox4x32_10_rk(ps.blk, dp.c1, dp.c2, dp.c3, dv, wa, wb, x2, x3);
+            ps.blk++;
+            ps.sx = x2; ps.sy = x3;
+            ps.half = 1u;
+        } else {
+            wa = ps.sx; wb = ps.sy;
+            ps.half = 0u;
+        }
+        bool ok0, ok1;
+        u32 g0 = ssd_fast_gap(f, wa, ok0), g1 = ssd_fast_gap(f, wb, ok1);
+        if (!(ok0 && ok1)) {  // within the margin of an integer (or shortcut off): the defining polynomial
+            if (!ok0) g0 = geom_gap(wa, f.inv);
+            if (!ok1) g1 = geom_gap(wb, f.inv);
+        }
+        const u32 incl = warp_scan_add(g0 + g1 + 2u);
+        ps.e1 = ps.last_p1 - 1u + incl;
+        ps.e0 = ps.e1 - 1u - g1;
+        ps.last_p1 = __reduce_max_sync(0xFFFFFFFFu, ps.e1) + 1u;  // lane 31's: positions ascend with the lane
+        ssd_fast_apply(f, ps.e0);
+        ssd_fast_apply(f, ps.e1);
     }
-    ps.evp = ps.evp < f.W ? 0xFFFFFFFFu : ps.evp - f.W;
-    ps.last_p1 -= f.W;
+    ps.e0 -= f.W;
+    ps.e1 -= f.W;
+    ps.last_p1 -= f.Wu;
     __syncwarp();
 }
 
@@ -1521,7 +1587,7 @@ __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdPerturb &p
 // the configuration the headline number is measured in.  Returns the number of iterations done (even).
 template <int TQ>
 __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const Col &st, Draw<PBN_DRAW_PHILOX> &d,
-                                                    Draw<PBN_DRAW_PHILOX> &dp, SsdPerturb &ps, SsdCount &cnt) {
+                                                    Draw<PBN_DRAW_PHILOX> &dp, SsdPerturb &ps0, SsdCount &cnt) {
     const NetView &nv = a.nv;
     SsdFast f;
     f.col = keep(smem_addr(st.s));
@@ -1533,11 +1599,13 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     f.shist = keep(smem_addr(a.shist));
     f.n = keep((u32)nv.n);
     f.W = keep((u32)nv.n * 32u);
+    f.Wu = (u32)nv.n * 32u;
     f.b_off = keep(((u32)a.sp.fast_t0 >> 5) << 10);
     f.b_sh = keep((u32)a.sp.fast_t0 & 31u);
     f.b_up = keep(32u - (u32)a.sp.g);
     f.inv = a.sp.inv;
     f.gdelta = 0.5f - a.sp.gdelta;  // the shortcut compares against 0.5 - margin (negative: never taken)
+    SsdFastPerturb ps{ps0.e0, ps0.e1, ps0.last_p1, dp.blk, 0u, 0u, 0u};  // (entered at the start of the loop: dp has no buffered words)
     u32 ublk = 0;
     int t = 0;
     u32 cur = (u32)cnt.cur, run = cnt.run;
@@ -1553,17 +1621,28 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
         u32 x0, x1, x2, x3;
         philox4x32_10_rk(ublk, d.c1, d.c2, d.c3, a.dv, x0, x1, x2, x3);
         ublk++;
+        // the draw half of an update does not depend on the state: issued ahead of the perturbation, its two dependent
+        // shared-memory loads are over when the state half needs them
+        const FastDraw da = ssd_fast_draw<TQ>(f, x0, x1);
         count();
         ssd_fast_perturb(f, ps, dp, a.dv);
-        ssd_fast_update<TQ>(f, x0, x1);
+        ssd_fast_apply_update(f, da);
         __syncwarp();
+        const FastDraw db = ssd_fast_draw<TQ>(f, x2, x3);
         count();
         ssd_fast_perturb(f, ps, dp, a.dv);
-        ssd_fast_update<TQ>(f, x2, x3);
+        ssd_fast_apply_update(f, db);
         __syncwarp();
     }
     d.blk = ublk;
     d.have = 0;
+    // hand the perturbation stream and the pending events back to the generic loop (an odd last iteration)
+    dp.blk = ps.blk;
+    dp.have = ps.half ? 2 : 0;
+    dp.b0 = ps.sx; dp.b1 = ps.sy;
+    ps0.e0 = ps.e0 >= 0x80000000u ? 0xFFFFFFFFu : ps.e0;
+    ps0.e1 = ps.e1 >= 0x80000000u ? 0xFFFFFFFFu : ps.e1;
+    ps0.last_p1 = ps.last_p1;
     cnt.cur = (int)cur; cnt.run = run;
     return t;
 }
@@ -1578,7 +1657,7 @@ __device__ __forceinline__ void ssd_loop(const SsdLoopArgs &a, const Col &st, Dr
     const float inv = sp.inv;
     const float hmd = 0.5f - sp.gdelta;  // gap shortcut: 0.5 - margin (negative: never taken)
     const bool flips = inv <= 0.f;
-    SsdPerturb ps{0xFFFFFFFFu, 0u};
+    SsdPerturb ps{0xFFFFFFFFu, 0xFFFFFFFFu, 0u};
     char *warp_cols = reinterpret_cast<char *>(a.sst + (threadIdx.x & ~31u));
     SsdCount cnt{active ? ssd_bucket(sp, a.s_tgt, st) : 0, 0u};
     int t = 0;
@@ -2217,7 +2296,7 @@ extern "C" int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, in
     if (chains == 0 || iters == 0) return PBN_OK;
     if (draws->mode == PBN_DRAW_PHILOX && p > 0 && (env0 & 31))
         return fail(PBN_ERR_ARG, "env0 must be a multiple of 32: the perturbation stream is shared by groups of 32 consecutive chain ids");
-    if (p > 0 && p < 1e-7) return fail(PBN_ERR_UNSUPPORTED, "bit_flip_prob below 1e-7 is not supported (gap law is truncated at 2^26)");
+    if (p > 0 && p < 1e-6) return fail(PBN_ERR_UNSUPPORTED, "bit_flip_prob below 1e-6 is not supported (gap law is truncated at 2^25)");
     const NetView &nv = net->v;
     const DrawView dv = make_draws(draws);
     SsdParams sp;

@@ -224,7 +224,7 @@ __device__ __forceinline__ float gap_uniform(u32 r) { return __fmaf_rn((float)(r
 __device__ __forceinline__ u32 geom_gap(u32 r, float inv) {
     float u = gap_uniform(r);
     float g = __fmul_rn(log2f_poly(u), inv);
-    if (!(g < 67108864.0f)) return 67108864u;  // gaps are capped at 2^26 so a warp prefix sum of 32 gaps fits 32 bits
+    if (!(g < 33554432.0f)) return 33554432u;  // gaps are capped at 2^25 so a warp prefix sum over a round's 64 gaps fits 32 bits
     return (u32)g;                              // g >= 0: truncation
 }
 

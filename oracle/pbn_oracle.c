@@ -182,7 +182,7 @@ static inline float orc_log2f_poly(float x) { /* x > 0, normal */
 uint32_t orc_geom(uint32_t r, float inv) {
     float u = ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
     float g = orc_log2f_poly(u) * inv;
-    if (!(g < 67108864.0f)) return 67108864u; /* capped at 2^26: 32 summed gaps fit 32 bits */
+    if (!(g < 33554432.0f)) return 33554432u; /* capped at 2^25: the 64 summed gaps of a round fit 32 bits */
     return (uint32_t)g;
 }
 float orc_geom_inv(double p) { /* host helper shared by tests: 1/log2(1-p) as float */
@@ -615,9 +615,10 @@ int orc_rand_state(const OrcNet *net, uint8_t *state, int64_t B, int64_t env0, c
    REPLAY: n doubles per chain per iteration, then the step's draws.
    PHILOX: the flips of each GROUP of 32 consecutive chain ids (global id >> 5) are one Bernoulli(p) renewal
    process over the interleaved index c = node*32 + lane, window = 32*n positions per iteration: in every round each
-   of the 32 lanes draws one geometric gap from its own PERTURBATION stream (Philox block indices from 2^31 on; the
-   update stream keeps block indices from 0 and is consumed at two words per update), event k of the round sits at
-   (last event) + sum of (1+gap) over lanes 0..k, and an event inside the window flips node c>>5 of chain c&31.
+   of the 32 lanes draws TWO geometric gaps from consecutive words of its own PERTURBATION stream (Philox block indices
+   from 2^31 on; the update stream keeps block indices from 0 and is consumed at two words per update), the 64 events of
+   a round are ordered lane-major (lane l holds events 2l and 2l+1), event k sits at (last event) + sum of (1+gap) over
+   events 0..k, and an event inside the window flips node c>>5 of chain c&31.
    That is the same law as n independent Bernoulli(p) draws per chain per iteration, at ~1 draw per chain.
    bucket = target-node bits MSB-first (pbn_target.py:383-391).  hist is uint64 [2^g], summed over chains. */
 int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains, int64_t env0, int64_t iters,
@@ -644,12 +645,12 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
         uint64_t *h = priv + (int64_t)tid * nb;
         const int64_t gb = gi * 32;
         Dr d[32], dp[32]; /* per chain: update stream, and perturbation stream (same key/counter words, block indices from 2^31) */
-        uint32_t ev[32], last_p1 = 0;
+        uint32_t ev[64], last_p1 = 0;
         for (int l = 0; l < 32; l++) {
             dr_init(&d[l], dr, gb + l < chains ? gb + l : 0, env0 + gb + l);
             dp[l] = d[l];
             dp[l].ctr[0] = 0x80000000u;
-            ev[l] = NONE;
+            ev[2 * l] = ev[2 * l + 1] = NONE;
         }
         for (int64_t t = 0; t < iters; t++) {
             for (int l = 0; l < 32 && gb + l < chains; l++) {
@@ -665,18 +666,18 @@ int orc_ssd(const OrcNet *net, const OrcEnv *env, uint8_t *state, int64_t chains
                 }
             } else if (flips) {
                 for (;;) {
-                    for (int l = 0; l < 32; l++)
-                        if (ev[l] < W) {
-                            uint32_t tl = ev[l] & 31u, bit = ev[l] >> 5;
+                    for (int k = 0; k < 64; k++)
+                        if (ev[k] < W) {
+                            uint32_t tl = ev[k] & 31u, bit = ev[k] >> 5;
                             if (gb + tl < chains) state[(gb + tl) * n + bit] ^= 1;
-                            ev[l] = NONE;
+                            ev[k] = NONE;
                         }
                     if (last_p1 > W) break;
                     uint32_t pre = 0;
-                    for (int l = 0; l < 32; l++) { pre += 1u + orc_geom(dr_u32(&dp[l]), inv); ev[l] = last_p1 - 1u + pre; }
-                    last_p1 = ev[31] + 1u;
+                    for (int k = 0; k < 64; k++) { pre += 1u + orc_geom(dr_u32(&dp[k >> 1]), inv); ev[k] = last_p1 - 1u + pre; }
+                    last_p1 = ev[63] + 1u;
                 }
-                for (int l = 0; l < 32; l++) if (ev[l] != NONE) ev[l] -= W;
+                for (int k = 0; k < 64; k++) if (ev[k] != NONE) ev[k] -= W;
                 last_p1 -= W;
             }
             for (int l = 0; l < 32 && gb + l < chains; l++) {
