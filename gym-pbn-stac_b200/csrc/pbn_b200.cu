@@ -389,35 +389,22 @@ __device__ __forceinline__ void ssd_fast_update(const SsdFast &f, u32 wa, u32 wb
 
 #include "pbn_coop.cuh"
 
-// the same update, predicated (`on`) and reporting the node, the old and the new word — for callers that track the state
+// the state half of an update, predicated (`on`) and reporting the old and the new word — for callers that track the state
 // incrementally (the lockstep first pass of the step-until-attractor envs keeps per-cube mismatch counts)
-template <int TQ>
-__device__ __forceinline__ void fast_update_io(const SsdFast &f, u32 wa, u32 wb, bool on, u32 &i, u32 &old, u32 &nw) {
-    i = __umulhi(wa, f.n);
-    const u32 r = wb >> 1;
-    u32 j16;
-    if constexpr (TQ == 1) {
-        j16 = count_le_x16(ldc_v4(f.thr + i * f.thr_stride), r);
-    } else {
-        const uint4 m = ldc_v4(f.thr + i * f.thr_stride);
-        u32 q = (m.x <= r) + (m.y <= r) + (m.z <= r) + (m.w <= r);
-        q = q < (u32)TQ - 1u ? q : (u32)TQ - 1u;
-        j16 = 64u * q + count_le_x16(ldc_v4(f.thr + i * f.thr_stride + 16u + q * 16u), r);
-    }
-    const uint4 rec = ldc_v4(f.rec + i * f.rec_stride + j16);
-    const u32 f1 = rec.x >> 16, f3 = rec.y >> 16;
-    const u32 w0 = lds_u32(f.col | (rec.x & 0x1C00u));
+__device__ __forceinline__ void fast_apply_io(const SsdFast &f, const FastDraw &d, bool on, u32 &old, u32 &nw) {
+    const u32 f1 = d.rx >> 16, f3 = d.ry >> 16;
+    const u32 w0 = lds_u32(f.col | (d.rx & 0x1C00u));
     const u32 w1 = lds_u32(f.col | (f1 & 0x1C00u));
-    const u32 w2 = lds_u32(f.col | (rec.y & 0x1C00u));
+    const u32 w2 = lds_u32(f.col | (d.ry & 0x1C00u));
     const u32 w3 = lds_u32(f.col | (f3 & 0x1C00u));
-    u32 idx = (__funnelshift_r(w0, w0, rec.x) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
-    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, rec.y) & ~0xCu);
+    u32 idx = (__funnelshift_r(w0, w0, d.rx) & 8u) | (__funnelshift_r(w1, w1, f1) & ~8u);
+    idx = (idx & 0xCu) | (__funnelshift_r(w2, w2, d.ry) & ~0xCu);
     idx = (idx & 0xEu) | (__funnelshift_r(w3, w3, f3) & ~0xEu);
-    const u32 v = __funnelshift_r(rec.z, 0u, idx);
-    const u32 wa_addr = f.col | ((i & ~31u) << 5);
-    const u32 m = __funnelshift_l(0u, 1u, i);
+    const u32 v = __funnelshift_r(d.rz, 0u, idx);
+    const u32 wa_addr = f.col | ((d.i & ~31u) << 5);
+    const u32 m = __funnelshift_l(0u, 1u, d.i);
     old = lds_u32(wa_addr);
-    nw = on ? (old & ~m) | (__funnelshift_l(0u, v, i) & m) : old;
+    nw = on ? (old & ~m) | (__funnelshift_l(0u, v, d.i) & m) : old;
     sts_u32(wa_addr, nw);
 }
 
@@ -1311,7 +1298,10 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
             hit_s0 = mm0 == 0 || mm1 == 0;
         }
     }
-    for (int t = 0;; t++) {  // t updates made so far by every running env
+    // One round = the attractor test of every running env, then one update.  The DRAW half of an update (node, predictor pick,
+    // record, and the cube words the incremental test needs) depends only on the stream: both rounds of a Philox block are drawn
+    // at once, ahead of the state halves, so that their dependent shared-memory loads are over when the state half starts.
+    auto test = [&](int t) {
         if (t > 0 && run) {
             // while not is_attracting_state(...): graph.step()  (pbn_target.py:270-271, pbn_target_multi.py:135-146; MULTI's
             // first test looks at the observation captured before the first update)
@@ -1321,13 +1311,14 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
             const bool done = (!multi && ev.force) || in >= ev.max_inner || hit || ev.n_att == 0;
             run = !done;
         }
-        if (t == pl.budget || !__any_sync(0xFFFFFFFFu, run)) break;
-        if ((t & 1) == 0) philox4x32_10_rk((u32)(t >> 1), dv.epoch, c2, c3, dv, x0, x1, x2, x3);
-        const u32 wa = (t & 1) ? x2 : x0, wb = (t & 1) ? x3 : x1;
+        return t == pl.budget || !__any_sync(0xFFFFFFFFu, run);
+    };
+    auto round = [&](u32 wa, u32 wb, const FastDraw &dr) {
         if constexpr (FAST) {
-            u32 i, old, nw;
-            fast_update_io<TQ>(f, wa, wb, run, i, old, nw);
+            u32 old, nw;
+            fast_apply_io(f, dr, run, old, nw);
             if (inc) {
+                const u32 i = dr.i;
                 const u32 flip = old ^ nw;  // the written bit, if it changed
                 const uint2 c0 = reinterpret_cast<const uint2 *>(cubes)[i >> 5];
                 mm0 += (flip & c0.x) ? (((nw ^ c0.y) & flip) ? 1 : -1) : 0;
@@ -1341,6 +1332,18 @@ __global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, Env
             micro_step_words<PBN_NET_PRED, TQ>(nv, blob, st, wa, wb, dummy);
             in++;
         }
+    };
+    for (int t = 0;; t += 2) {  // t updates made so far by every running env
+        if (test(t)) break;
+        philox4x32_10_rk((u32)(t >> 1), dv.epoch, c2, c3, dv, x0, x1, x2, x3);
+        FastDraw da{}, db{};
+        if constexpr (FAST) {
+            da = ssd_fast_draw<TQ>(f, x0, x1);
+            db = ssd_fast_draw<TQ>(f, x2, x3);
+        }
+        round(x0, x1, da);
+        if (test(t + 1)) break;
+        round(x2, x3, db);
     }
     if (valid && run) {  // out of budget: park the env for a resume pass
         store_state(st, state, B, e, w32);
