@@ -368,7 +368,10 @@ def test_philox_tt_env_step_matches_oracle(eng, kind):
         assert np.array_equal(sim.inner.cpu().numpy(), inner)
 
 
-@pytest.mark.parametrize("which,p", [("100_5_kmeans", 0.01), ("28_15_median", 0.05), ("200_5_kmeans", 0.0), ("tt", 1.0)])
+@pytest.mark.parametrize("which,p", [("100_5_kmeans", 0.01), ("28_15_median", 0.05), ("200_5_kmeans", 0.0), ("tt", 1.0),
+                                     # the static loop at its extremes: several rounds of the perturbation process per
+                                     # iteration, and rounds thousands of iterations apart (applied event slots stay stale)
+                                     ("100_5_kmeans", 0.3), ("100_5_kmeans", 1e-5), ("100_5_kmeans", 1e-6)])
 def test_philox_ssd_matches_oracle(eng, which, p):
     net, onet = _nets(eng, which)
     B, iters, seed = 3000, 400, 99
@@ -429,6 +432,15 @@ def test_philox_ssd_with_attractor_loop(eng):
     ohist = orc.ssd(onet, oenv, ost, iters, 0.01, tgt, orc.Draws(seed=seed, epoch=1))
     assert np.array_equal(hist.cpu().numpy().astype(np.uint64), ohist)
     assert np.array_equal(_state_np(sim), ost)
+
+
+def test_flip_probability_below_the_gap_cap_is_refused(eng):
+    """Gaps are capped at 2^25 (the 64 summed gaps of a round must fit 32 bits); the cap would bite below p = 1e-6."""
+    net, _ = _nets(eng, "100_5_kmeans")
+    sim = eng.engine.Simulator(net, 64, seed=1)
+    sim.rand_state()
+    with pytest.raises(eng.abi.PbnError):
+        sim.ssd(4, 5e-7, np.arange(7, dtype=np.int32))
 
 
 def test_large_g_uses_global_histogram(eng):
