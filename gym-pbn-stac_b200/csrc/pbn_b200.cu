@@ -1239,8 +1239,11 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
 // the update of the asynchronous rollout kernel (ssd_fast_update: one LOP3 per gather address, rotate-merge LUT index) and
 // an INCREMENTAL attractor test — a mismatch count per cube that moves by -1, 0 or +1 with the one bit an update writes,
 // instead of comparing every state word with every cube after every update.
+#ifndef PBN_FIRST_MIN_BLOCKS
+#define PBN_FIRST_MIN_BLOCKS 3
+#endif
 template <int TQ, bool FAST>
-__global__ void __launch_bounds__(PBN_BLOCK, 3) k_env_step_first(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+__global__ void __launch_bounds__(PBN_BLOCK, PBN_FIRST_MIN_BLOCKS) k_env_step_first(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                               int *target_att, const int *actions, int K, u32 *obs_state,
                                                               int *reward, unsigned char *terminated, unsigned char *truncated,
                                                               int *inner_steps, long long B, long long env0, PlanView pl, VecView vx) {
