@@ -328,7 +328,6 @@ struct SsdFast {
     u32 thr_stride, rec_stride;  // bytes per node
     u32 shist;      // shared address of the block histogram
     u32 n, W;
-    u32 Wu;         // W again, not pinned in a vector register
     u32 b_off, b_sh, b_up;  // bucket field: word offset, right shift, left shift (32 - g)
     float inv, gdelta;  // gdelta: 0.5 - margin of the gap shortcut
 };
@@ -1558,7 +1557,7 @@ __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdFastPertur
     ssd_fast_apply(f, ps.e1);
     // last_p1 comes out of a warp reduction: the compiler knows it is the same in every lane and branches on it without
     // reconvergence code
-    while (ps.last_p1 <= f.Wu) {  // every pending event lay inside this window and has just been applied: the next round
+    while (ps.last_p1 <= f.W) {  // every pending event lay inside this window and has just been applied: the next round
         u32 wa, wb;
         if (ps.half == 0u) {  // a round takes two words: every second one computes a block
             u32 x2, x3;
@@ -1585,7 +1584,7 @@ __device__ __forceinline__ void ssd_fast_perturb(const SsdFast &f, SsdFastPertur
     }
     ps.e0 -= f.W;
     ps.e1 -= f.W;
-    ps.last_p1 -= f.Wu;
+    ps.last_p1 -= f.W;
     __syncwarp();
 }
 
@@ -1605,7 +1604,6 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
     f.shist = keep(smem_addr(a.shist));
     f.n = keep((u32)nv.n);
     f.W = keep((u32)nv.n * 32u);
-    f.Wu = (u32)nv.n * 32u;
     f.b_off = keep(((u32)a.sp.fast_t0 >> 5) << 10);
     f.b_sh = keep((u32)a.sp.fast_t0 & 31u);
     f.b_up = keep(32u - (u32)a.sp.g);
@@ -1623,7 +1621,7 @@ __device__ __forceinline__ int ssd_loop_pred_static(const SsdLoopArgs &a, const 
         cur = b;
         run = r0 + 1u;
     };
-    for (; t + 1 < a.iters; t += 2) {
+    for (int left = a.iters >> 1; left > 0; left--, t += 2) {  // (a count-down: the bound is not re-read from the parameter bank)
         u32 x0, x1, x2, x3;
         philox4x32_10_rk(ublk, d.c1, d.c2, d.c3, a.dv, x0, x1, x2, x3);
         ublk++;
