@@ -361,6 +361,16 @@ class Simulator:
                 c["plans"] = [abi.PbnStepPlan(running=_ptr(self.running), work=_ptr(self._work), budget=b, resume=int(k > 0), phase=k & 1)
                               for k, b in enumerate(self._passes(env))]
                 c["fn2"] = abi.lib().pbn_env_step_plan
+                if autoreset and len(c["plans"]) > 1:
+                    # A step of several passes resets its finished envs in ONE masked launch after the last pass instead of
+                    # inside the passes: in group mode the lane that finishes an env would otherwise run the reset (pair
+                    # sampling, wildcard bits, state write-back) alone while the other envs of its warp wait for it.
+                    # Same draws (reset_draws, the step's second epoch), same result as the fused reset.
+                    c["v_nr"] = abi.PbnVecState.from_buffer_copy(v)
+                    c["v_nr"].autoreset = 0
+                    c["rd"] = rd
+                    c["mask"] = torch.zeros(self.B, dtype=torch.bool, device=self.device)
+                    c["cur"] = curriculum
         d, v = c["d"], c["v"]
         d.seed = v.reset_draws.seed = self.seed
         v.reset_draws.mode = abi.DRAW_PHILOX
@@ -374,11 +384,27 @@ class Simulator:
         with on_device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             if "plans" in c:
+                vv = c.get("v_nr", v)
                 for plan in c["plans"]:
-                    rc = c["fn2"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(v), C.byref(plan), self.B,
+                    rc = c["fn2"](*c["head"], C.c_void_p(actions.data_ptr()), K, *c["tail"], C.byref(vv), C.byref(plan), self.B,
                                   self.env0, C.byref(d), stream)
                     if rc:
                         abi.check(rc)
+                    self.launches += 1
+                if "v_nr" in c:
+                    rd, mask, cur = c["rd"], c["mask"], c["cur"]
+                    rd.seed, rd.epoch, rd.epoch_dev = v.reset_draws.seed, v.reset_draws.epoch, v.reset_draws.epoch_dev
+                    torch.bitwise_or(self.terminated, self.truncated, out=mask)
+                    if cur:
+                        rc = abi.lib().pbn_env_reset_cur(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                                         _ptr(self.target_state), _ptr(mask), _ptr(cur[0]), _ptr(cur[1]),
+                                                         int(bool(cur[2])), self.B, self.env0, C.byref(rd), stream)
+                    else:
+                        rc = abi.lib().pbn_env_reset(env.handle, _ptr(self.state), _ptr(self.n_steps), _ptr(self.target_att),
+                                                     _ptr(self.target_state), _ptr(mask), self.B, self.env0, C.byref(rd), stream)
+                    if rc:
+                        abi.check(rc)
+                    torch.where(mask, self.state, self.obs_state, out=self.obs_state)  # reset envs observe their new state
                     self.launches += 1
                 self._auto_sample()
                 return
