@@ -204,7 +204,8 @@ def test_multi_env_list_and_tensor_actions():
             break
 
 
-def test_vector_env_matches_oracle():
+@pytest.mark.parametrize("plan", [None, (3, 8)])
+def test_vector_env_matches_oracle(plan):
     import gym_PBN
     from gym_PBN.b200.vector_env import PBNVectorEnv
 
@@ -213,6 +214,8 @@ def test_vector_env_matches_oracle():
     env = gym_PBN.make("gym-PBN/Bittner-28-v0", all_attractors=atts, max_inner_steps=32)
     B, seed = 4096, 17
     vec = PBNVectorEnv(env, B, seed=seed)
+    if plan is not None:  # planned step: three passes + the masked reset launch (Simulator.vec_step)
+        vec.sim.plan_budgets = plan
     obs, info = vec.reset()
     sets, ids = orc.load_bittner("28_15_median")
     onet = orc.net_from_predictor_sets(sets, ids)
@@ -838,8 +841,8 @@ def test_self_triggering_prob_is_clamped():
     assert int(info["interval"].min()) >= 1 and int(info["interval"].max()) < 500
 
 
-@pytest.mark.parametrize("sample_pair", [False, True])
-def test_vector_env_curriculum_matches_oracle(sample_pair):
+@pytest.mark.parametrize("sample_pair,plan", [(False, None), (True, None), (True, (4, 16))])
+def test_vector_env_curriculum_matches_oracle(sample_pair, plan):
     """Device-side curriculum of PBNTargetMultiEnv (pbn_target_multi.py:159-181, 232-235): every env's own probability row is
     reworked when its episode ends and the reset draws the attractor pair from it — product (fused in the step launch) vs the
     oracle (step, then per finished env rework_probas + reset), bit for bit, float64 rows included."""
@@ -857,6 +860,8 @@ def test_vector_env_curriculum_matches_oracle(sample_pair):
     env = gym_PBN.make("gym-PBN/BittnerMulti-28-v0", all_attractors=atts, max_inner_steps=40, horizon=25, sample_pair=sample_pair)
     B, seed = 1500, 31
     vec = PBNVectorEnv(env, B, seed=seed, curriculum=True, action_slots=2)
+    if plan is not None:  # a step of several budgeted passes: finished envs are reset by ONE masked launch after the last pass
+        vec.sim.plan_budgets = plan
     obs, info = vec.reset()
     sets, ids = orc.load_bittner("28_15_median")
     onet = orc.net_from_predictor_sets(sets, ids)
