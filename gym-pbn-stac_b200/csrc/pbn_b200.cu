@@ -953,6 +953,9 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
 #ifndef PBN_COOP_EXIT_AT
 #define PBN_COOP_EXIT_AT 2  // group mode, queue not empty: stopped groups at which a call returns to finalize / refill
 #endif
+#ifndef PBN_COOP_WIDE_FACTOR
+#define PBN_COOP_WIDE_FACTOR 1  // a resume list longer than this many times 8 envs per warp runs 16 envs per warp
+#endif
 
 // is_attracting without early exits (the lockstep first pass: a warp's lanes test together, a branch per cube only diverges)
 __device__ __forceinline__ bool is_attracting_flat(const EnvView &ev, const int *att_off, const u32 *cubes, const Col &st, int w32) {
@@ -1070,23 +1073,31 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
     int quota = 8;
     long long static_n = 0, per_slot = 0;  // list positions dealt out statically (resume passes), in rounds of per_slot
     bool warp_on = true;
+    // owners sit on every fourth lane (8 envs per warp, groups of >= 4 lanes) — or, in a resume pass whose list would keep every
+    // warp queueing, on every second lane: 16 envs per warp in groups of two lanes.  An entry costs the warp the same
+    // instructions whatever the group width, so narrow groups double the envs served per instruction; their update takes
+    // longer (the draw half of a batch is amortised over 8 entries instead of 16), which only pays while the pass is bound by
+    // throughput, and every lane then tests up to two cubes itself, so only for envs with at most four cubes.
+    int osh = 2;
     if (resume) {
         const long long nb = gridDim.x;
         int A = hi <= nb * 4 * 8 ? 4 : 8;
         if (pl.dbg_a > 0) A = pl.dbg_a;
+        if (grp && A == 8 && hi > nb * 8 * 8 * PBN_COOP_WIDE_FACTOR && ev.n_att > 0 && att_off[ev.n_att] <= 4) osh = 1;
+        const int qmax = 32 >> osh;
         const long long q = (hi + nb * A - 1) / (nb * A);
-        quota = q < 1 ? 1 : (q > 8 ? 8 : (int)q);
+        quota = q < 1 ? 1 : (q > qmax ? qmax : (int)q);
         per_slot = nb * A;
         static_n = quota * per_slot;
         warp_on = (int)(threadIdx.x >> 5) < A;
     }
-    const bool owner_lane = !grp || ((threadIdx.x & 3) == 0 && (int)((threadIdx.x & 31) >> 2) < quota);
+    const bool owner_lane = !grp || ((threadIdx.x & ((1u << osh) - 1u)) == 0 && (int)((threadIdx.x & 31) >> osh) < quota);
     long long e = 0, nxt = hi;
     if (owner_lane) {
         if (!resume) nxt = lo + (grp ? threadIdx.x >> 2 : threadIdx.x);
         else if (!grp) nxt = (long long)atomicAdd(&pl.list_in[1], 1);  // (lane mode: every lane pulls)
         else if (warp_on)  // consecutive positions go to different blocks, i.e. SMs, first
-            nxt = (long long)((threadIdx.x & 31) >> 2) * per_slot + (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+            nxt = (long long)((threadIdx.x & 31) >> osh) * per_slot + (long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     }
     if (resume && !grp) static_n = 0;
     int used = 0;  // updates made for the current env in this launch (budget)
@@ -1192,7 +1203,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
             if (coop_on && hv != 0u && (grp || (__popc(live) <= PBN_COOP_MAX && drained))) {
                 const int nl = __popc(hv);
                 int k = 1;
-                while (k < nl) k <<= 1;                 // groups: 1, 2, 4 or 8
+                while (k < nl) k <<= 1;                 // groups: 1, 2, 4, 8 (or 16 in a wide resume pass)
                 const int g = 32 / k;                   // lanes per group
                 const int grp = (int)lane / g;
                 const bool active = grp < nl;
@@ -1208,7 +1219,7 @@ __global__ void __launch_bounds__(PBN_BLOCK, 2) k_env_step_att(NetView nv, EnvVi
                 // the call returns when `exit_at` groups have stopped: their owners finalize on the next trip (and, while the
                 // block's queue lasts, start the next env), the other envs come back here — in wider groups once the queue
                 // is empty, which is why the first stop ends the call then
-                const int exit_at = drained ? 1 : PBN_COOP_EXIT_AT;
+                const int exit_at = drained ? 1 : (k > 8 ? 2 * PBN_COOP_EXIT_AT : PBN_COOP_EXIT_AT);
                 const int fin = coop_steps<TQ, W1>(nv, ev, dv, blob, att_off, cubes, colL, env0 + eL, inL, stop_in, active, g, 0u, wb, exit_at);
                 __syncwarp();
                 for (int r = 0; r < nl; r++) {          // hand each group's count back to the lane that owns the env

@@ -25,9 +25,10 @@
 #define PBN_COOP_ENTRY_BYTES 32  // {g0, g1, g2, g3} {Lrot, mask, word address, cube word offset}
 // per-warp staging bytes: the entries (+ 16 bytes of padding per group: the groups of a warp read the same entry index at the
 // same time, and regions a multiple of 128 bytes apart would put all those 16-byte reads on the same four banks) + one
-// checkpoint column (w32 words) for each of up to 8 groups
-#define PBN_COOP_ENT_BYTES (PBN_COOP_ENTRIES * PBN_COOP_ENTRY_BYTES + 8 * 16)
-__host__ __device__ inline int coop_warp_bytes(int w32) { return PBN_COOP_ENT_BYTES + ((8 * w32 * 4 + 15) & ~15); }
+// checkpoint column (w32 words) for each of up to 16 groups
+#define PBN_COOP_GROUPS_MAX 16   // groups of two lanes: the throughput end of the trade (resume passes with long lists)
+#define PBN_COOP_ENT_BYTES (PBN_COOP_ENTRIES * PBN_COOP_ENTRY_BYTES + PBN_COOP_GROUPS_MAX * 16)
+__host__ __device__ inline int coop_warp_bytes(int w32) { return PBN_COOP_ENT_BYTES + ((PBN_COOP_GROUPS_MAX * w32 * 4 + 15) & ~15); }
 
 __device__ __forceinline__ uint4 lds_v4(u32 a) {
     uint4 v;
