@@ -176,6 +176,42 @@ def test_step_plan_split_invariance(eng, name, kind, n_act, care, budgets):
             assert parked[0] > 0 and inner.max() > budgets[0]  # the split actually happened
 
 
+@pytest.mark.parametrize("name,kind,n_act", [("200_5_kmeans", "multi", 3), ("28_15_median", "target", 1)])
+def test_step_plan_two_lane_groups(eng, name, kind, n_act):
+    """A resume pass whose list exceeds 8 envs per warp over the whole grid runs 16 envs per warp in groups of TWO lanes (envs
+    with at most four cubes): same words, same result as the oracle's unsplit step."""
+    net = eng.engine.Network(eng.compiler.load_bittner(name))
+    sets, ids = orc.load_bittner(name)
+    onet = orc.net_from_predictor_sets(sets, ids)
+    n, B, seed = net.n, 80000, 23
+    rng = np.random.default_rng(seed)
+    atts = []
+    for a in range(2):  # two single-cube attractors; cubes that care about many nodes: an intervention often leaves them
+        c = ["*"] * n
+        for i in rng.choice(n, size=n // 2 if n < 64 else 40, replace=False):
+            c[i] = int(rng.integers(0, 2))
+        atts.append([tuple(c)])
+    multi = kind == "multi"
+    env = eng.engine.EnvImage(net, eng.abi.ENV_MULTI if multi else eng.abi.ENV_TARGET, attractors=atts, horizon=100, max_inner=400, dedup=True)
+    oenv = orc.Env(orc.ENV_MULTI if multi else orc.ENV_TARGET, n, attractors=atts, horizon=100, max_inner=400, dedup=1)
+    sim = eng.engine.Simulator(net, B, seed=seed)
+    ost, ons, ota = np.zeros((B, n), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    sim.env_reset(env)
+    orc.env_reset(onet, oenv, ost, ons, ota, orc.Draws(seed=seed, epoch=0))
+    for t in range(2):
+        act = rng.integers(0, n + 1, size=(B, n_act)).astype(np.int32)
+        sim.env_step(env, torch.from_numpy(act), budget=2)
+        assert int(sim.running.sum()) > 148 * 2 * 8 * 8  # longer than 8 envs per warp on every SM: the wide pass
+        sim.env_step_resume(env, budget=0)
+        assert int(sim.running.sum()) == 0
+        obs, rew, term, trunc, inner = orc.env_step(onet, oenv, ost, ons, ota, act, orc.Draws(seed=seed, epoch=1 + t))
+        assert np.array_equal(sim.unpack().cpu().numpy(), ost)
+        assert np.array_equal(sim.unpack(sim.obs_state).cpu().numpy(), obs)
+        assert np.array_equal(sim.reward.cpu().numpy(), rew) and np.array_equal(sim.inner.cpu().numpy(), inner)
+        assert np.array_equal(sim.terminated.cpu().numpy(), term) and np.array_equal(sim.truncated.cpu().numpy(), trunc)
+        assert inner.max() == 400  # cap hits included
+
+
 def test_step_plan_matches_single_launch(eng):
     """The two-pass default of Simulator.env_step against the one-launch kernel (plan_budgets = ()), cap hits included."""
     B, seed = 20000, 5
