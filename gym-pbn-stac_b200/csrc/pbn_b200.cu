@@ -807,6 +807,39 @@ __device__ __forceinline__ int pbcn_reward(const EnvView &ev, const int *att_off
     return -ev.wrong_attractor_cost * m;
 }
 
+// The same tests through 32-bit shared-window addresses held in registers.  Through generic pointers ptxas re-derives the
+// window base (S2R SR_CgaCtaId, LEA) inside the cube loops — 46 instructions per attractor where 12 do — and k_env_step runs
+// these loops after EVERY update of a sampled-data / self-triggering macro step.
+struct CubeView {
+    u32 cubes, att_off, col;  // shared addresses: cube table, attractor offsets, this thread's state column
+    int w32;
+};
+__device__ __forceinline__ bool cube_match_sa(const CubeView &cv, int c) {
+    const u32 pa = cv.cubes + (u32)c * (u32)cv.w32 * 8u;
+    for (int w = 0; w < cv.w32; w++) {  // early exit per word: a many-care cube fails in its first words
+        const uint2 cw = ldc_v2(pa + 8u * (u32)w);
+        if ((lds_u32(cv.col + 1024u * (u32)w) & cw.x) != cw.y) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ bool match_range_sa(const CubeView &cv, int c0, int c1) {
+    for (int c = c0; c < c1; c++)
+        if (cube_match_sa(cv, c)) return true;
+    return false;
+}
+__device__ __forceinline__ int pbcn_reward_sa(const EnvView &ev, const CubeView &cv, int &term) {
+    if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { term = 1; return ev.successful_reward; }
+    int m = 0;
+    int c0 = (int)lds_u32(cv.att_off);
+    for (int a = 0; a < ev.n_att; a++) {
+        const int c1 = (int)lds_u32(cv.att_off + 4u * (u32)(a + 1));
+        m += match_range_sa(cv, c0, c1) ? 1 : 0;
+        c0 = c1;
+    }
+    term = 0;
+    return -ev.wrong_attractor_cost * m;
+}
+
 template <int NET, int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
@@ -829,6 +862,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     if (e < B) load_state(st, state, B, e, w32);
     __syncthreads();
     if (e < B) {
+    const CubeView cv{keep(smem_addr(cubes)), keep(smem_addr(att_off)), keep(smem_addr(st.s)), w32};
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
     const int *act = actions + e * K;
@@ -839,21 +873,21 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
         int a = act[0];
         if (a != 0) flip_node(st, a, nv.n, bad);  // flips index `action` itself (Q3)
         micro_step<NET, MODE>(nv, blob, st, d); in = 1;
-        if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew = 20; tm = 1; }
+        if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { rew = 20; tm = 1; }
         else rew = -4 - (a != 0);
     } break;
     case PBN_ENV_PBCN: {  // pbcn_env.py:67-80
         int a = act[0];
         if (a != 0) flip_node(st, a, nv.n, bad);
         micro_step<NET, MODE>(nv, blob, st, d); in = 1;
-        rew = pbcn_reward(ev, att_off, cubes, st, w32, tm);
+        rew = pbcn_reward_sa(ev, cv, tm);
     } break;
     case PBN_ENV_PBN_SD: {  // sampled_data.py:52-88
         int a = act[0], interval = act[1];
         for (int i = 0; i < interval; i++) {
             if (a != 0) flip_node(st, a - 1, nv.n, bad);
             micro_step<NET, MODE>(nv, blob, st, d); in++;
-            if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { rew += 20; tm = 1; }
+            if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { rew += 20; tm = 1; }
             else { rew += -4 - (a != 0); tm = 0; }
         }
     } break;
@@ -872,7 +906,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
                     for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
             }
             micro_step<NET, MODE>(nv, blob, st, d); in++;
-            int r = pbcn_reward(ev, att_off, cubes, st, w32, tm) - 1;  // time_step_cost = 1
+            int r = pbcn_reward_sa(ev, cv, tm) - 1;  // time_step_cost = 1
             if (tstep >= 0) r -= ev.successful_reward;                // overshoot penalty
             else if (tm) tstep = i;
             rew += r;
@@ -898,7 +932,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
             if (!pbcn) {
                 if (a != 0) flip_node(st, a - 1, nv.n, bad);
                 micro_step<NET, MODE>(nv, blob, st, d);
-                if (match_range(cubes, ev.tgt_first, ev.tgt_first + ev.n_tgt, st, w32)) { r = 20; tm = 1; }
+                if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { r = 20; tm = 1; }
                 else { r = -4 - (a != 0); tm = 0; }
             } else {
                 if (ev.control_write) {
@@ -907,7 +941,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
                         for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
                 }
                 micro_step<NET, MODE>(nv, blob, st, d);
-                r = pbcn_reward(ev, att_off, cubes, st, w32, tm) - 1;  // time step cost
+                r = pbcn_reward_sa(ev, cv, tm) - 1;  // time step cost
             }
             total += ev.gamma_pow[i < ev.n_gamma ? i : ev.n_gamma - 1] * (double)r;  // total_reward += gamma**i * reward
             i++;
