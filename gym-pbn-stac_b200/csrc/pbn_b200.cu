@@ -840,6 +840,33 @@ __device__ __forceinline__ int pbcn_reward_sa(const EnvView &ev, const CubeView 
     return -ev.wrong_attractor_cost * m;
 }
 
+// One asynchronous update of a truth-table network (Node.compute_next_value common/node.py:31-38, PBN.step common/pbn.py:88-92,
+// PBCN.step common/pbcn.py:59-61) through shared-window addresses held in registers; same words, same result as micro_step.
+struct TtView {
+    u32 node, in, thr, col;  // shared addresses: node records, input lists, threshold table (unused with thr_dev), state column
+    const u32 *thr_dev;
+    u32 first, span;         // the updated node is first + mulhi(word, span)
+};
+__device__ __forceinline__ void tt_micro_step_sa(const TtView &tv, Draw<PBN_DRAW_PHILOX> &d) {
+    const u32 i = tv.first + __umulhi(d.next(), tv.span);
+    const uint2 nr = ldc_v2(tv.node + 8u * i);  // (table offset, input offset | k << 16)
+    const u32 k = nr.y >> 16;
+    u32 ia = tv.in + 2u * (nr.y & 0xFFFFu);
+    u32 idx = 0;
+    for (u32 q = 0; q < k; q++, ia += 2u) {
+        u32 pos;
+        asm("ld.shared.u16 %0, [%1];" : "=r"(pos) : "r"(ia));
+        const u32 w = lds_u32(tv.col + ((pos & ~31u) << 5));
+        idx = (idx << 1) | ((w >> (pos & 31u)) & 1u);
+    }
+    const u32 thr = tv.thr_dev ? __ldg(tv.thr_dev + nr.x + idx) : lds_u32(tv.thr + 4u * (nr.x + idx));
+    const u32 v = ((d.next() >> 1) < thr) ? 1u : 0u;
+    const u32 wa = tv.col + ((i & ~31u) << 5);
+    const u32 m = 1u << (i & 31u);
+    const u32 old = lds_u32(wa);
+    sts_u32(wa, v ? (old | m) : (old & ~m));
+}
+
 template <int NET, int MODE>
 __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
@@ -863,8 +890,14 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     __syncthreads();
     if (e < B) {
     const CubeView cv{keep(smem_addr(cubes)), keep(smem_addr(att_off)), keep(smem_addr(st.s)), w32};
+    const TtView tv{keep(smem_addr(blob + nv.off_node)), keep(smem_addr(blob + nv.off_in)), keep(smem_addr(blob + nv.off_thr)), cv.col,
+                    nv.thr_dev, (u32)nv.first, (u32)(nv.n - nv.first)};
     Draw<MODE> d;
     d.init(dv, e, env0 + e);
+    auto update = [&]() {
+        if constexpr (NET == PBN_NET_TT && MODE == PBN_DRAW_PHILOX) tt_micro_step_sa(tv, d);
+        else micro_step<NET, MODE>(nv, blob, st, d);
+    };
     const int *act = actions + e * K;
     int rew = 0, tm = 0, tr = 0, in = 0, bad = 0;
     double rew_d = 0.0;
@@ -872,21 +905,21 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
     case PBN_ENV_PBN: {  // pbn_env.py:141-154, reward :171-183
         int a = act[0];
         if (a != 0) flip_node(st, a, nv.n, bad);  // flips index `action` itself (Q3)
-        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        update(); in = 1;
         if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { rew = 20; tm = 1; }
         else rew = -4 - (a != 0);
     } break;
     case PBN_ENV_PBCN: {  // pbcn_env.py:67-80
         int a = act[0];
         if (a != 0) flip_node(st, a, nv.n, bad);
-        micro_step<NET, MODE>(nv, blob, st, d); in = 1;
+        update(); in = 1;
         rew = pbcn_reward_sa(ev, cv, tm);
     } break;
     case PBN_ENV_PBN_SD: {  // sampled_data.py:52-88
         int a = act[0], interval = act[1];
         for (int i = 0; i < interval; i++) {
             if (a != 0) flip_node(st, a - 1, nv.n, bad);
-            micro_step<NET, MODE>(nv, blob, st, d); in++;
+            update(); in++;
             if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { rew += 20; tm = 1; }
             else { rew += -4 - (a != 0); tm = 0; }
         }
@@ -905,7 +938,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
                 else
                     for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
             }
-            micro_step<NET, MODE>(nv, blob, st, d); in++;
+            update(); in++;
             int r = pbcn_reward_sa(ev, cv, tm) - 1;  // time_step_cost = 1
             if (tstep >= 0) r -= ev.successful_reward;                // overshoot penalty
             else if (tm) tstep = i;
@@ -931,7 +964,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
             int r;
             if (!pbcn) {
                 if (a != 0) flip_node(st, a - 1, nv.n, bad);
-                micro_step<NET, MODE>(nv, blob, st, d);
+                update();
                 if (match_range_sa(cv, ev.tgt_first, ev.tgt_first + ev.n_tgt)) { r = 20; tm = 1; }
                 else { r = -4 - (a != 0); tm = 0; }
             } else {
@@ -940,7 +973,7 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
                     else
                         for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
                 }
-                micro_step<NET, MODE>(nv, blob, st, d);
+                update();
                 r = pbcn_reward_sa(ev, cv, tm) - 1;  // time step cost
             }
             total += ev.gamma_pow[i < ev.n_gamma ? i : ev.n_gamma - 1] * (double)r;  // total_reward += gamma**i * reward
