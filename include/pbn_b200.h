@@ -215,7 +215,10 @@ int pbn_env_reset_cur(const PbnEnv *env, uint32_t *state, int32_t *n_steps, int3
 int pbn_rand_state(const PbnNet *net, uint32_t *state, int64_t B, int64_t env0, const PbnDraws *draws, void *stream);
 
 /* K3 — utils/eval.py:76-103 _ssd_run for `chains` chains x `iters` iterations (model=None), histogram summed over
-   chains into hist[2^g] (uint64, accumulated: caller zeroes).  env may be NULL (= one update per iteration). */
+   chains into hist[2^g] (uint64, accumulated: caller zeroes).  env may be NULL (= one update per iteration).
+   bit_flip_prob is 0 (no perturbation) or in [1e-6, 1]: with Philox draws the flips of eval.py:92-95 are drawn as geometric
+   gaps (capped at 2^25 positions, which a smaller probability would reach), PBN_ERR_UNSUPPORTED below that; Philox-mode
+   shards must start at a multiple of 32 chain ids (env0 % 32 == 0: one perturbation process per 32 consecutive chains). */
 int pbn_ssd(const PbnNet *net, const PbnEnv *env, uint32_t *state, int64_t chains, int64_t env0, int64_t iters,
             double bit_flip_prob, const int32_t *tgt_nodes_host, int32_t g, uint64_t *hist, const PbnDraws *draws,
             void *stream);
