@@ -847,8 +847,14 @@ struct TtView {
     const u32 *thr_dev;
     u32 first, span;         // the updated node is first + mulhi(word, span)
 };
+__device__ __forceinline__ void tt_micro_step_words_sa(const TtView &tv, u32 wa, u32 wb);
 __device__ __forceinline__ void tt_micro_step_sa(const TtView &tv, Draw<PBN_DRAW_PHILOX> &d) {
-    const u32 i = tv.first + __umulhi(d.next(), tv.span);
+    const u32 wa = d.next(), wb = d.next();
+    tt_micro_step_words_sa(tv, wa, wb);
+}
+// the same update from two given words of the env's update stream (wa picks the node, wb decides)
+__device__ __forceinline__ void tt_micro_step_words_sa(const TtView &tv, u32 wa, u32 wb) {
+    const u32 i = tv.first + __umulhi(wa, tv.span);
     const uint2 nr = ldc_v2(tv.node + 8u * i);  // (table offset, input offset | k << 16)
     const u32 k = nr.y >> 16;
     u32 ia = tv.in + 2u * (nr.y & 0xFFFFu);
@@ -860,15 +866,15 @@ __device__ __forceinline__ void tt_micro_step_sa(const TtView &tv, Draw<PBN_DRAW
         idx = (idx << 1) | ((w >> (pos & 31u)) & 1u);
     }
     const u32 thr = tv.thr_dev ? __ldg(tv.thr_dev + nr.x + idx) : lds_u32(tv.thr + 4u * (nr.x + idx));
-    const u32 v = ((d.next() >> 1) < thr) ? 1u : 0u;
-    const u32 wa = tv.col + ((i & ~31u) << 5);
+    const u32 v = ((wb >> 1) < thr) ? 1u : 0u;
+    const u32 wd = tv.col + ((i & ~31u) << 5);
     const u32 m = 1u << (i & 31u);
-    const u32 old = lds_u32(wa);
-    sts_u32(wa, v ? (old | m) : (old & ~m));
+    const u32 old = lds_u32(wd);
+    sts_u32(wd, v ? (old | m) : (old & ~m));
 }
 
 template <int NET, int MODE>
-__global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
+__global__ void __launch_bounds__(PBN_BLOCK, 4) k_env_step(NetView nv, EnvView ev, DrawView dv, u32 *state, int *n_steps,
                                                         const int *target_att, const int *actions, int K, u32 *obs_state,
                                                         int *reward, unsigned char *terminated, unsigned char *truncated,
                                                         int *inner_steps, long long B, long long env0, VecView vx, double *rew_f64) {
@@ -932,17 +938,33 @@ __global__ void __launch_bounds__(PBN_BLOCK) k_env_step(NetView nv, EnvView ev, 
         const u32 cmask = ev.n_control >= 32 ? 0xFFFFFFFFu : ((1u << ev.n_control) - 1u);
         if (ev.control_write && ev.n_control <= 32)
             for (int c = 0; c < ev.n_control; c++) cbits |= (act[1 + c] != 0 ? 1u : 0u) << c;
-        for (int i = 0; i < interval; i++) {
+        auto one = [&](int i, auto &&step) {
             if (ev.control_write) {
                 if (ev.n_control <= 32) st.set_word(0, (st.word(0) & ~cmask) | cbits);
                 else
                     for (int c = 0; c < ev.n_control; c++) st.put(c, act[1 + c] != 0);
             }
-            update(); in++;
+            step(); in++;
             int r = pbcn_reward_sa(ev, cv, tm) - 1;  // time_step_cost = 1
             if (tstep >= 0) r -= ev.successful_reward;                // overshoot penalty
             else if (tm) tstep = i;
             rew += r;
+        };
+        if constexpr (NET == PBN_NET_TT && MODE == PBN_DRAW_PHILOX) {
+            // an update takes exactly two words of the env's stream: one Philox block per two updates, no buffer bookkeeping
+            u32 blk = d.blk;  // (0: the stream starts with this step)
+            int i = 0;
+            for (; i + 1 < interval; i += 2) {
+                u32 x0, x1, x2, x3;
+                philox4x32_10_rk(blk++, d.c1, d.c2, d.c3, dv, x0, x1, x2, x3);
+                one(i, [&]() { tt_micro_step_words_sa(tv, x0, x1); });
+                one(i + 1, [&]() { tt_micro_step_words_sa(tv, x2, x3); });
+            }
+            d.blk = blk;
+            d.have = 0;
+            if (i < interval) one(i, [&]() { tt_micro_step_sa(tv, d); });  // odd tail: the stream object takes over
+        } else {
+            for (int i = 0; i < interval; i++) one(i, update);
         }
     } break;
     case PBN_ENV_PBN_ST:     // self_triggering.py:56-93: (action, prob 1..10)
